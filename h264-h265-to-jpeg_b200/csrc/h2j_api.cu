@@ -1,0 +1,682 @@
+// C ABI of h2j_b200 (include/h2j_b200.h): host-side orchestration of the kernels in h2j_kernels.cuh.
+// Pure CUDA runtime; no torch types, no CPU encode path.
+#include "../../include/h2j_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "h2j_kernels.cuh"
+
+using namespace h2j;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct KernelTiming {
+    const char *name;
+    cudaEvent_t start, stop;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    uint8_t *d_frames = nullptr;  // staging for host submits
+    int16_t *d_coefs = nullptr;
+    unsigned long long *d_masks = nullptr;
+    int16_t *d_dcs = nullptr;
+    uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket — zeroed every batch
+    size_t zero_bytes = 0;
+    FrameState *d_state = nullptr;
+    unsigned long long *d_descs = nullptr;
+    unsigned int *d_ticket = nullptr;
+    FrameTab *d_tabs = nullptr;
+    uint32_t *d_scan = nullptr;
+    uint8_t *d_out = nullptr;
+    uint8_t *d_packed = nullptr;
+    unsigned long long *d_offsets = nullptr;
+    int *d_status = nullptr;
+    unsigned long long *h_offsets = nullptr;  // pinned
+    int *h_status = nullptr;                  // pinned
+    long long *h_sizes = nullptr;             // pinned (jpeg_bytes per frame)
+    uint8_t *h_stage = nullptr;               // pinned staging for h2j_encode_frame / convert
+    size_t h_stage_bytes = 0;
+    bool busy = false;
+    int n = 0;
+    FrameLayout L{};
+    std::vector<KernelTiming> timings;
+    int timings_used = 0;
+};
+
+}  // namespace
+
+struct h2j_encoder {
+    h2j_settings s{};
+    std::string comment;
+    std::string err;
+    int sm_count = 0;
+    size_t out_cap = 0;           // per-frame JPEG capacity (multiple of 16)
+    long long scan_cap_words = 0;
+    long long blocks_cap = 0;     // blocks per frame at max geometry, rounded up to whole FDCT tiles
+    int tiles_cap = 0;            // entropy tiles per frame at max geometry
+    size_t frame_bytes_cap = 0;
+    uint8_t *d_qscale_lut = nullptr;
+    char *d_comment = nullptr;
+    std::vector<Slot> slots;
+    long long launches = 0;
+};
+
+namespace {
+
+int fail(h2j_encoder *e, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(e, call)                                                                                       \
+    do {                                                                                                  \
+        cudaError_t err__ = (call);                                                                       \
+        if (err__ != cudaSuccess)                                                                         \
+            return fail((e), H2J_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- first-frame rate control tail, folded into a table over i_tex_bits -----------------------------
+// libavcodec/ratecontrol.c (FFmpeg 6fd0116): ff_rate_estimate_qscale -> get_qscale ("tex^qComp") ->
+// get_diff_limited_q (no-op for the first I picture) -> intra-only blur -> modify_qscale -> clip ->
+// (int)(q + 0.5); then mpegvideo_enc.c update_qscale().  All AVCodecContext fields at their defaults, as
+// reference src/Encoder.cpp leaves them (it only sets time_base = 1/25, which cancels out for picture 0).
+int qscale_from_i_tex_bits(int n)
+{
+    const float rce_qscale = 118 * 2;                    // FF_QP2LAMBDA * 2
+    const float qcompress = 0.5f, qblur = 0.5f;
+    const float i_quant_factor = -0.8f, i_quant_offset = 0.0f;
+    const int lmin = 2 * 118, lmax = 31 * 118;
+    int qmin = (int)(lmin * std::fabs((double)i_quant_factor) + i_quant_offset + 0.5);
+    int qmax = (int)(lmax * std::fabs((double)i_quant_factor) + i_quant_offset + 0.5);
+    const double rate_factor = 0.001 / 0.001 * 1.0f;     // pass1_wanted_bits / pass1_rc_eq_output_sum * br_compensation
+    const double tex = (double)n * (double)rce_qscale;
+    double bits = std::pow(tex, (double)qcompress);
+    bits *= rate_factor;
+    if (bits < 0.0) bits = 0.0;
+    bits += 1.0;
+    double qd = rce_qscale * (double)(n + 1) / bits;     // bits2qp
+    qd = -qd * i_quant_factor + i_quant_offset;
+    if (qd < 1) qd = 1;
+    float q = (float)qd;
+    double qsum = 0.001, qcount = 0.001;                 // short-term blur (intra_only)
+    qsum *= qblur;
+    qcount *= qblur;
+    qsum += q;
+    qcount++;
+    q = (float)(qsum / qcount);
+    double qm = q;                                       // modify_qscale
+    if (qm < qmin) qm = qmin;
+    else if (qm > qmax) qm = qmax;
+    q = (float)qm;
+    if (q < qmin) q = (float)qmin;
+    else if (q > qmax) q = (float)qmax;
+    q = (float)(int)(q + 0.5);
+    return lambda_to_qscale((int)q);
+}
+
+uint8_t range_lut_value(int s, bool chroma)  // libswscale lumRangeToJpeg_c / chrRangeToJpeg_c + round
+{
+    int v = s << 7;
+    if (!chroma) { if (v > 30189) v = 30189; v = (v * 19077 - 39057361) >> 14; }
+    else { if (v > 30775) v = 30775; v = (v * 4663 - 9289992) >> 12; }
+    v = (v + 64) >> 7;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t tight_frame_bytes(int w, int h) { return (size_t)w * h + 2 * (size_t)((w + 1) >> 1) * ((h + 1) >> 1); }
+
+int make_layout(h2j_encoder *e, const uint8_t *base, size_t frame_stride, int w, int h, FrameLayout *L)
+{
+    if (w < 2 || h < 2 || w > 65500 || h > 65500) return fail(e, H2J_ERR_UNSUPPORTED, "unsupported frame size %dx%d", w, h);
+    if (w > e->s.max_width || h > e->s.max_height)
+        return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum %dx%d", w, h, e->s.max_width, e->s.max_height);
+    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
+    L->w = w; L->h = h; L->cw = w >> 1; L->ch = h >> 1;
+    L->y_pitch = w; L->c_pitch = fcw;
+    L->u_off = (long long)w * h;
+    L->v_off = L->u_off + (long long)fcw * fch;
+    L->frame_stride = (long long)frame_stride;
+    L->mcu_w = (w + 15) >> 4; L->mcu_h = (h + 15) >> 4;
+    L->n_mcu = L->mcu_w * L->mcu_h;
+    L->n_blocks = L->n_mcu * 6;
+    auto al = [&](int a) {
+        return ((uintptr_t)base % a) == 0 && (frame_stride % a) == 0 && (L->u_off % a) == 0 && (L->v_off % a) == 0 &&
+               (L->y_pitch % a) == 0 && (L->c_pitch % a) == 0;
+    };
+    L->aligned8 = al(8) ? 1 : 0;
+    L->aligned16 = ((uintptr_t)base % 16) == 0 && (frame_stride % 16) == 0 && (L->y_pitch % 16) == 0 ? 1 : 0;
+    L->range_mode = e->s.range_mode;
+    L->fixed_qscale = e->s.fixed_qscale;
+    return H2J_OK;
+}
+
+struct ScopedTiming {
+    Slot &sl;
+    bool on;
+    int idx = -1;
+    ScopedTiming(h2j_encoder *e, Slot &s, const char *name) : sl(s), on(e->s.profile != 0)
+    {
+        if (!on) return;
+        if (sl.timings_used == (int)sl.timings.size()) {
+            KernelTiming t{name, nullptr, nullptr};
+            cudaEventCreate(&t.start);
+            cudaEventCreate(&t.stop);
+            sl.timings.push_back(t);
+        }
+        idx = sl.timings_used++;
+        sl.timings[idx].name = name;
+        cudaEventRecord(sl.timings[idx].start, sl.stream);
+    }
+    ~ScopedTiming() { if (on) cudaEventRecord(sl.timings[idx].stop, sl.stream); }
+};
+
+// Enqueue the whole pipeline for `n` frames at `d_frames` on the slot's stream.
+int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n)
+{
+    const FrameLayout &L = sl.L;
+    cudaStream_t st = sl.stream;
+    sl.timings_used = 0;
+    CU(e, cudaMemsetAsync(sl.d_zero, 0, sl.zero_bytes, st));
+    {
+        ScopedTiming t(e, sl, "mbvar_kernel");
+        mbvar_kernel<<<dim3(L.mcu_h, n), 128, 0, st>>>(d_frames, L, sl.d_state);
+        e->launches++;
+    }
+    {
+        ScopedTiming t(e, sl, "frame_setup_kernel");
+        frame_setup_kernel<<<n, 64, 0, st>>>(L, sl.d_state, e->d_qscale_lut, sl.d_tabs);
+        e->launches++;
+    }
+    {
+        ScopedTiming t(e, sl, "fdct_quant_kernel");
+        const int n_tiles = (L.n_mcu + kFdctMcusPerTile - 1) / kFdctMcusPerTile;
+        const int tiles_per_cta = 4;
+        fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, 0, st>>>(
+            d_frames, L, sl.d_tabs, sl.d_state, sl.d_coefs, sl.d_masks, sl.d_dcs, e->blocks_cap, tiles_per_cta);
+        e->launches++;
+    }
+    {
+        ScopedTiming t(e, sl, "huffman_kernel");
+        huffman_kernel<<<n, kHuffThreads, 4 * sizeof(HuffScratch), st>>>(L, sl.d_tabs, sl.d_state, sl.d_dcs, e->blocks_cap, sl.d_out,
+                                                                       (long long)e->out_cap, e->d_comment, (int)e->comment.size());
+        e->launches++;
+    }
+    const int tiles_per_frame = (L.n_blocks + kEntropyThreads - 1) / kEntropyThreads;
+    {
+        ScopedTiming t(e, sl, "entropy_kernel");
+        entropy_kernel<<<tiles_per_frame * n, kEntropyThreads, (kEntropyBufWords + 2) * sizeof(unsigned int), st>>>(
+            L, sl.d_tabs, sl.d_state, sl.d_coefs, sl.d_masks, sl.d_dcs, e->blocks_cap, sl.d_descs, sl.d_ticket, tiles_per_frame, sl.d_scan,
+            e->scan_cap_words);
+        e->launches++;
+    }
+    {
+        ScopedTiming t(e, sl, "stuff_kernel");
+        stuff_kernel<<<n, kStuffThreads, 0, st>>>(sl.d_tabs, sl.d_state, sl.d_scan, e->scan_cap_words, sl.d_out, (long long)e->out_cap);
+        e->launches++;
+    }
+    CU(e, cudaGetLastError());
+    return H2J_OK;
+}
+
+int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
+{
+    cudaStream_t st = sl.stream;
+    {
+        ScopedTiming t(e, sl, "pack_offsets_kernel");
+        pack_offsets_kernel<<<1, 32, 0, st>>>(sl.d_tabs, sl.n, (long long)e->out_cap, sl.d_offsets, sl.d_status);
+        e->launches++;
+    }
+    if (pack) {
+        ScopedTiming t(e, sl, "pack_kernel");
+        pack_kernel<<<dim3(8, sl.n), 256, 0, st>>>(sl.d_out, (long long)e->out_cap, sl.d_offsets, sl.d_packed);
+        e->launches++;
+    }
+    CU(e, cudaMemcpyAsync(sl.h_offsets, sl.d_offsets, sizeof(unsigned long long) * (sl.n + 1), cudaMemcpyDeviceToHost, st));
+    CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int) * sl.n, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaGetLastError());
+    return H2J_OK;
+}
+
+int check_slot(h2j_encoder *e, int slot)
+{
+    if (!e) return H2J_ERR_INVALID_ARG;
+    if (slot < 0 || slot >= (int)e->slots.size()) return fail(e, H2J_ERR_INVALID_ARG, "slot %d out of range (n_slots %d)", slot, (int)e->slots.size());
+    return H2J_OK;
+}
+
+void free_slot(Slot &sl)
+{
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFree(sl.d_frames); cudaFree(sl.d_coefs); cudaFree(sl.d_masks); cudaFree(sl.d_dcs); cudaFree(sl.d_zero);
+    cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
+    if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
+    if (sl.h_status) cudaFreeHost(sl.h_status);
+    if (sl.h_sizes) cudaFreeHost(sl.h_sizes);
+    if (sl.h_stage) cudaFreeHost(sl.h_stage);
+    for (auto &t : sl.timings) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    sl = Slot{};
+}
+
+}  // namespace
+
+extern "C" {
+
+void h2j_default_settings(h2j_settings *s)
+{
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    s->device = 0;
+    s->max_width = 1920;
+    s->max_height = 1088;
+    s->max_batch = 16;
+    s->n_slots = 2;
+    s->range_mode = H2J_RANGE_PASSTHROUGH;
+    s->fixed_qscale = 0;
+    s->max_jpeg_bytes = 0;
+    s->comment = nullptr;
+    s->profile = 0;
+}
+
+int h2j_abi_version(void) { return H2J_ABI_VERSION; }
+
+const char *h2j_status_string(int status)
+{
+    switch (status) {
+    case H2J_OK: return "ok";
+    case H2J_ERR_INVALID_ARG: return "invalid argument";
+    case H2J_ERR_CUDA: return "CUDA error";
+    case H2J_ERR_UNSUPPORTED: return "unsupported geometry";
+    case H2J_ERR_OUTPUT_TOO_SMALL: return "output buffer too small";
+    case H2J_ERR_BUSY: return "slot busy / nothing to collect";
+    case H2J_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+const char *h2j_last_error(const h2j_encoder *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+long long h2j_kernel_launches(const h2j_encoder *e) { return e ? e->launches : 0; }
+
+void *h2j_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void h2j_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+void h2j_destroy(h2j_encoder *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->s.device);
+    for (auto &sl : e->slots) free_slot(sl);
+    cudaFree(e->d_qscale_lut);
+    cudaFree(e->d_comment);
+    delete e;
+}
+
+int h2j_create(const h2j_settings *s, h2j_encoder **out)
+{
+    if (!s || !out) return fail(nullptr, H2J_ERR_INVALID_ARG, "null settings/out");
+    *out = nullptr;
+    if (s->max_width < 2 || s->max_height < 2 || s->max_width > 65500 || s->max_height > 65500 || s->max_batch < 1 || s->n_slots < 1 ||
+        s->n_slots > 8 || s->fixed_qscale < 0 || s->fixed_qscale > 31 || (s->range_mode != 0 && s->range_mode != 1))
+        return fail(nullptr, H2J_ERR_INVALID_ARG, "bad settings");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, H2J_ERR_CUDA, "no usable CUDA device (%s); h2j_b200 has no CPU path", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (s->device < 0 || s->device >= ndev) return fail(nullptr, H2J_ERR_INVALID_ARG, "device %d out of range (%d devices)", s->device, ndev);
+    h2j_encoder *e = new h2j_encoder();
+    e->s = *s;
+    e->comment = s->comment ? s->comment : "Lavc58.117.101";
+    e->s.comment = nullptr;
+    auto bail = [&](int code) { std::string m = e->err; h2j_destroy(e); g_create_error = m; return code; };
+#define CUB(call)                                                                                                   \
+    do {                                                                                                            \
+        cudaError_t err__ = (call);                                                                                 \
+        if (err__ != cudaSuccess) {                                                                                 \
+            fail(e, H2J_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__);   \
+            return bail(err__ == cudaErrorMemoryAllocation ? H2J_ERR_NOMEM : H2J_ERR_CUDA);                          \
+        }                                                                                                           \
+    } while (0)
+    CUB(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, s->device));
+    e->sm_count = prop.multiProcessorCount;
+
+    e->out_cap = align_up(s->max_jpeg_bytes ? s->max_jpeg_bytes : (size_t)2 * 1024 * 1024, 16);
+    e->scan_cap_words = (long long)(e->out_cap / 4);
+    const int mcu_w = (s->max_width + 15) >> 4, mcu_h = (s->max_height + 15) >> 4;
+    const long long n_mcu = (long long)mcu_w * mcu_h;
+    e->blocks_cap = (n_mcu + kFdctMcusPerTile - 1) / kFdctMcusPerTile * kFdctThreads;
+    e->tiles_cap = (int)((n_mcu * 6 + kEntropyThreads - 1) / kEntropyThreads);
+    e->frame_bytes_cap = align_up(tight_frame_bytes(s->max_width, s->max_height), 256);
+
+    // constant tables
+    {
+        uint8_t lut[2][256];
+        for (int i = 0; i < 256; i++) { lut[0][i] = range_lut_value(i, false); lut[1][i] = range_lut_value(i, true); }
+        CUB(cudaMemcpyToSymbol(c_range_lut, lut, sizeof lut));
+        std::vector<uint8_t> q(kQscaleLutSize);
+        for (int n = 0; n < kQscaleLutSize; n++) q[n] = (uint8_t)qscale_from_i_tex_bits(n);
+        CUB(cudaMalloc(&e->d_qscale_lut, kQscaleLutSize));
+        CUB(cudaMemcpy(e->d_qscale_lut, q.data(), kQscaleLutSize, cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&e->d_comment, e->comment.size() + 1));
+        CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
+    }
+    CUB(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
+    CUB(cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kEntropyBufWords + 2) * sizeof(unsigned int))));
+
+    const int B = s->max_batch;
+    e->slots.resize(s->n_slots);
+    for (auto &sl : e->slots) {
+        CUB(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CUB(cudaEventCreate(&sl.ev_begin));
+        CUB(cudaEventCreate(&sl.ev_done));
+        CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
+        CUB(cudaMalloc(&sl.d_coefs, (size_t)e->blocks_cap * B * 64 * sizeof(int16_t)));
+        CUB(cudaMalloc(&sl.d_masks, (size_t)e->blocks_cap * B * sizeof(unsigned long long)));
+        CUB(cudaMalloc(&sl.d_dcs, (size_t)e->blocks_cap * B * sizeof(int16_t)));
+        const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
+        const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->tiles_cap * B, 256);
+        sl.zero_bytes = state_bytes + desc_bytes + 256;
+        CUB(cudaMalloc(&sl.d_zero, sl.zero_bytes));
+        sl.d_state = reinterpret_cast<FrameState *>(sl.d_zero);
+        sl.d_descs = reinterpret_cast<unsigned long long *>(sl.d_zero + state_bytes);
+        sl.d_ticket = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes);
+        CUB(cudaMalloc(&sl.d_tabs, sizeof(FrameTab) * B));
+        CUB(cudaMalloc(&sl.d_scan, (size_t)e->scan_cap_words * 4 * B));
+        CUB(cudaMalloc(&sl.d_out, e->out_cap * B));
+        CUB(cudaMalloc(&sl.d_packed, e->out_cap * B));
+        CUB(cudaMalloc(&sl.d_offsets, sizeof(unsigned long long) * (B + 1)));
+        CUB(cudaMalloc(&sl.d_status, sizeof(int) * B));
+        CUB(cudaHostAlloc(&sl.h_offsets, sizeof(unsigned long long) * (B + 1), cudaHostAllocDefault));
+        CUB(cudaHostAlloc(&sl.h_status, sizeof(int) * B, cudaHostAllocDefault));
+        CUB(cudaHostAlloc(&sl.h_sizes, sizeof(long long) * B, cudaHostAllocDefault));
+    }
+    // single-frame staging (slot 0 only): planes in, JPEG / padded planes out
+    {
+        Slot &s0 = e->slots[0];
+        const size_t padded = (size_t)mcu_w * 16 * mcu_h * 16 * 3 / 2;
+        s0.h_stage_bytes = std::max(std::max(e->frame_bytes_cap, e->out_cap), padded);
+        CUB(cudaHostAlloc(&s0.h_stage, s0.h_stage_bytes, cudaHostAllocDefault));
+    }
+#undef CUB
+    *out = e;
+    return H2J_OK;
+}
+
+int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int n, int width, int height)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
+    if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
+    if (frame_stride < tight_frame_bytes(width, height)) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
+    CU(e, cudaSetDevice(e->s.device));
+    rc = make_layout(e, d_frames, frame_stride, width, height, &sl.L);
+    if (rc) return rc;
+    sl.n = n;
+    CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
+    rc = launch_pipeline(e, sl, d_frames, n);
+    if (rc) return rc;
+    sl.busy = true;
+    return H2J_OK;
+}
+
+int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t frame_stride, int n, int width, int height)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
+    if (!frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
+    const size_t fb = tight_frame_bytes(width, height);
+    if (frame_stride < fb) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
+    CU(e, cudaSetDevice(e->s.device));
+    // device copy keeps frames at a 256-byte aligned stride so the vector-load paths apply
+    const size_t dstride = align_up(fb, 256);
+    if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
+    rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
+    if (rc) return rc;
+    sl.n = n;
+    CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
+    if (frame_stride == dstride) CU(e, cudaMemcpyAsync(sl.d_frames, frames, dstride * (n - 1) + fb, cudaMemcpyHostToDevice, sl.stream));
+    else CU(e, cudaMemcpy2DAsync(sl.d_frames, dstride, frames, frame_stride, fb, n, cudaMemcpyHostToDevice, sl.stream));
+    rc = launch_pipeline(e, sl, sl.d_frames, n);
+    if (rc) return rc;
+    sl.busy = true;
+    return H2J_OK;
+}
+
+int h2j_wait(h2j_encoder *e, int slot)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(e->slots[slot].stream));
+    return H2J_OK;
+}
+
+int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, size_t *offsets, int *status)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
+    if (!out || !offsets) return fail(e, H2J_ERR_INVALID_ARG, "null out/offsets");
+    CU(e, cudaSetDevice(e->s.device));
+    rc = enqueue_pack_and_sizes(e, sl, true);
+    if (rc) { sl.busy = false; return rc; }
+    CU(e, cudaStreamSynchronize(sl.stream));
+    sl.busy = false;
+    const size_t total = (size_t)sl.h_offsets[sl.n];
+    int worst = H2J_OK;
+    for (int i = 0; i <= sl.n; i++) offsets[i] = (size_t)sl.h_offsets[i];
+    for (int i = 0; i < sl.n; i++) {
+        if (status) status[i] = sl.h_status[i];
+        if (sl.h_status[i] != 0) worst = sl.h_status[i];
+    }
+    if (total > out_capacity) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "batch needs %zu bytes, caller gave %zu", total, out_capacity);
+    CU(e, cudaMemcpyAsync(out, sl.d_packed, total, cudaMemcpyDeviceToHost, sl.stream));
+    CU(e, cudaEventRecord(sl.ev_done, sl.stream));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    if (worst != H2J_OK) return fail(e, worst, "at least one frame failed: %s", h2j_status_string(worst));
+    return H2J_OK;
+}
+
+int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *d_frame_capacity, size_t *sizes, int *status)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
+    CU(e, cudaSetDevice(e->s.device));
+    rc = enqueue_pack_and_sizes(e, sl, false);
+    if (rc) { sl.busy = false; return rc; }
+    CU(e, cudaEventRecord(sl.ev_done, sl.stream));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    sl.busy = false;
+    int worst = H2J_OK;
+    for (int i = 0; i < sl.n; i++) {
+        if (sizes) sizes[i] = (size_t)(sl.h_offsets[i + 1] - sl.h_offsets[i]);
+        if (status) status[i] = sl.h_status[i];
+        if (sl.h_status[i] != 0) worst = sl.h_status[i];
+    }
+    if (d_out) *d_out = sl.d_out;
+    if (d_frame_capacity) *d_frame_capacity = e->out_cap;
+    if (worst != H2J_OK) return fail(e, worst, "at least one frame failed: %s", h2j_status_string(worst));
+    return H2J_OK;
+}
+
+int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height, uint8_t *out,
+                     size_t out_capacity, size_t *out_size)
+{
+    if (!e) return H2J_ERR_INVALID_ARG;
+    if (!planes || !strides || !planes[0] || !planes[1] || !planes[2] || !out || !out_size)
+        return fail(e, H2J_ERR_INVALID_ARG, "null plane/out pointer");
+    if (width < 2 || height < 2 || width > e->s.max_width || height > e->s.max_height)
+        return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d outside 2x2 .. %dx%d", width, height, e->s.max_width, e->s.max_height);
+    Slot &sl = e->slots[0];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
+    const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
+    if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
+    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels)
+    uint8_t *p = sl.h_stage;
+    for (int r = 0; r < height; r++) memcpy(p + (size_t)r * width, planes[0] + (size_t)r * strides[0], width);
+    p += (size_t)width * height;
+    for (int pl = 1; pl <= 2; pl++) {
+        for (int r = 0; r < fch; r++) memcpy(p + (size_t)r * fcw, planes[pl] + (size_t)r * strides[pl], fcw);
+        p += (size_t)fcw * fch;
+    }
+    const size_t fb = tight_frame_bytes(width, height);
+    int rc = h2j_submit_host(e, 0, sl.h_stage, align_up(fb, 256), 1, width, height);
+    if (rc) return rc;
+    size_t offs[2] = {0, 0};
+    int st = 0;
+    // JPEG comes back through the pinned staging buffer when it fits, so the D2H copy is a true async DMA
+    uint8_t *dst = (e->out_cap <= sl.h_stage_bytes) ? sl.h_stage : out;
+    const size_t dcap = (dst == out) ? out_capacity : sl.h_stage_bytes;
+    rc = h2j_collect(e, 0, dst, dcap, offs, &st);
+    if (rc) return rc;
+    *out_size = offs[1];
+    if (offs[1] > out_capacity) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "JPEG is %zu bytes, caller gave %zu", offs[1], out_capacity);
+    if (dst != out) memcpy(out, dst, offs[1]);
+    return H2J_OK;
+}
+
+int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height, int range_mode,
+                    uint8_t *out_y, uint8_t *out_u, uint8_t *out_v)
+{
+    if (!e) return H2J_ERR_INVALID_ARG;
+    if (!planes || !strides || !out_y || !out_u || !out_v) return fail(e, H2J_ERR_INVALID_ARG, "null pointer");
+    if (width < 2 || height < 2 || width > e->s.max_width || height > e->s.max_height)
+        return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d outside the configured maximum", width, height);
+    Slot &sl = e->slots[0];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
+    CU(e, cudaSetDevice(e->s.device));
+    const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
+    uint8_t *p = sl.h_stage;
+    for (int r = 0; r < height; r++) memcpy(p + (size_t)r * width, planes[0] + (size_t)r * strides[0], width);
+    p += (size_t)width * height;
+    for (int pl = 1; pl <= 2; pl++) {
+        for (int r = 0; r < fch; r++) memcpy(p + (size_t)r * fcw, planes[pl] + (size_t)r * strides[pl], fcw);
+        p += (size_t)fcw * fch;
+    }
+    const size_t fb = tight_frame_bytes(width, height);
+    FrameLayout L;
+    int rc = make_layout(e, sl.d_frames, align_up(fb, 256), width, height, &L);
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(sl.d_frames, sl.h_stage, fb, cudaMemcpyHostToDevice, sl.stream));
+    const int pw = L.mcu_w * 16, ph = L.mcu_h * 16;
+    // padded planes are produced in the (otherwise idle) JPEG output buffer
+    const size_t need = (size_t)pw * ph * 3 / 2;
+    if (need > e->out_cap * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's output buffer");
+    uint8_t *oy = sl.d_out, *ou = oy + (size_t)pw * ph, *ov = ou + (size_t)pw * ph / 4;
+    convert_pad_kernel<<<dim3((pw / 16 + 127) / 128, ph, 3), 128, 0, sl.stream>>>(sl.d_frames, L, range_mode, oy, ou, ov);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemcpyAsync(out_y, oy, (size_t)pw * ph, cudaMemcpyDeviceToHost, sl.stream));
+    CU(e, cudaMemcpyAsync(out_u, ou, (size_t)pw * ph / 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU(e, cudaMemcpyAsync(out_v, ov, (size_t)pw * ph / 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    return H2J_OK;
+}
+
+int h2j_debug_frame_info(h2j_encoder *e, int slot, int frame, h2j_frame_info *info)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (!info || frame < 0 || frame >= sl.n) return fail(e, H2J_ERR_INVALID_ARG, "bad frame index %d", frame);
+    CU(e, cudaSetDevice(e->s.device));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    FrameTab t;
+    FrameState st;
+    CU(e, cudaMemcpy(&t, sl.d_tabs + frame, sizeof t, cudaMemcpyDeviceToHost));
+    CU(e, cudaMemcpy(&st, sl.d_state + frame, sizeof st, cudaMemcpyDeviceToHost));
+    memset(info, 0, sizeof *info);
+    info->qscale = t.qscale;
+    info->mb_var_sum = t.mb_var_sum;
+    info->mcu_w = sl.L.mcu_w;
+    info->mcu_h = sl.L.mcu_h;
+    info->header_bytes = t.header_bytes;
+    info->scan_bits = t.scan_bits;
+    info->stuffed_ff = t.stuffed_ff;
+    memcpy(info->intra_matrix, t.intra, 64);
+    memcpy(info->hist, st.hist, sizeof info->hist);
+    memcpy(info->bits, t.bits, sizeof info->bits);
+    memcpy(info->vals, t.vals, sizeof info->vals);
+    memcpy(info->nvals, t.nvals, sizeof info->nvals);
+    return H2J_OK;
+}
+
+int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, size_t out_elems)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (!out || frame < 0 || frame >= sl.n) return fail(e, H2J_ERR_INVALID_ARG, "bad frame index %d", frame);
+    const size_t need = (size_t)sl.L.n_blocks * 64;
+    if (out_elems < need) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "need %zu int16 elements", need);
+    CU(e, cudaSetDevice(e->s.device));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    CU(e, cudaMemcpy(out, sl.d_coefs + (size_t)frame * e->blocks_cap * 64, need * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return H2J_OK;
+}
+
+int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, int cap)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    CU(e, cudaSetDevice(e->s.device));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    int n = 0;
+    for (int i = 0; i < sl.timings_used && n < cap; i++, n++) {
+        float t = 0.f;
+        CU(e, cudaEventElapsedTime(&t, sl.timings[i].start, sl.timings[i].stop));
+        if (names) names[n] = sl.timings[i].name;
+        if (ms) ms[n] = t;
+    }
+    return n;
+}
+
+int h2j_slot_total_ms(h2j_encoder *e, int slot, float *ms)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (!ms) return fail(e, H2J_ERR_INVALID_ARG, "null ms");
+    CU(e, cudaSetDevice(e->s.device));
+    CU(e, cudaEventSynchronize(sl.ev_done));
+    CU(e, cudaEventElapsedTime(ms, sl.ev_begin, sl.ev_done));
+    return H2J_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+/*
+ * h2j_b200 — B200-native (sm_100a) JPEG encoder for the YUV -> JPEG stage of
+ * BornToDeath/h264-h265-to-jpeg, behind a plain C ABI.
+ *
+ * What it replaces in the reference (file:line in /root/reference):
+ *   src/Encoder.cpp:89-297   Encoder::yuv2Jpeg(AVFrame*)  — avcodec "mjpeg" encoder opened with
+ *                            pix_fmt YUVJ420P (:150), time_base 1/25 (:190), defaults otherwise,
+ *                            avcodec_send_frame (:239) / avcodec_receive_packet (:248), raw "mjpeg" muxer
+ *                            write (:262), bytes gathered through writeCallback (:27) into a 2 MiB buffer
+ *                            (src/Common.h:15 HEAP_SIZE) and saved with saveJpegtoFile (:336).
+ *   src/Decoder.cpp:319      the only call site: Encoder(outputFilePath).yuv2Jpeg(frame).
+ * Everything in front of it (src/Decoder.cpp libavformat/libavcodec H.264/H.265 decode) and the public
+ * surface (export_inc/IDecoder.h, src/jni/...) stay the reference's own code.
+ *
+ * The bytes produced are identical to what the reference writes for the same decoded planes: same
+ * quantised coefficients, same optimal Huffman tables, same header, same stuffing.
+ *
+ * All entry points return 0 (H2J_OK) or a negative h2j_status.  No CPU fallback exists: if no CUDA
+ * device is usable h2j_create fails with H2J_ERR_CUDA.
+ */
+#ifndef H2J_B200_H
+#define H2J_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2J_ABI_VERSION 1
+
+typedef enum h2j_status {
+    H2J_OK = 0,
+    H2J_ERR_INVALID_ARG = -1,     /* null pointer, non-positive size, batch larger than configured ... */
+    H2J_ERR_CUDA = -2,            /* a CUDA runtime call failed; see h2j_last_error() */
+    H2J_ERR_UNSUPPORTED = -3,     /* geometry outside max_width/max_height, width or height < 2 or > 65500 */
+    H2J_ERR_OUTPUT_TOO_SMALL = -4,/* a JPEG did not fit max_jpeg_bytes / the caller's buffer */
+    H2J_ERR_BUSY = -5,            /* slot already has a batch in flight, or nothing to collect */
+    H2J_ERR_NOMEM = -6
+} h2j_status;
+
+/* How the planes are interpreted before encoding. */
+typedef enum h2j_range_mode {
+    /* Planes go to the encoder as they are.  This is what reference src/Encoder.cpp does: it never calls
+     * sws_scale; a yuv420p AVFrame is handed to an encoder opened as yuvj420p (Encoder.cpp:150, :239). */
+    H2J_RANGE_PASSTHROUGH = 0,
+    /* yuv420p (limited) -> yuvj420p (full) first, bit-exact with libswscale 5.8.100's unscaled
+     * lumRangeToJpeg/chrRangeToJpeg path (what a sws_scale call in front of the encoder would produce). */
+    H2J_RANGE_LIMITED_TO_FULL = 1
+} h2j_range_mode;
+
+typedef struct h2j_settings {
+    int device;            /* CUDA device ordinal */
+    int max_width;         /* largest frame the encoder will be asked for */
+    int max_height;
+    int max_batch;         /* frames per submitted batch (>= 1) */
+    int n_slots;           /* batches that may be in flight at once, each on its own stream (1..8) */
+    int range_mode;        /* h2j_range_mode */
+    int fixed_qscale;      /* 0: the reference's first-frame rate control decides (default);
+                              1..31: force it (AV_CODEC_FLAG_QSCALE equivalent; not used by the reference) */
+    size_t max_jpeg_bytes; /* per-frame output capacity; 0 = 2 MiB, the reference's HEAP_SIZE */
+    const char *comment;   /* COM segment payload; NULL = "Lavc58.117.101", the LIBAVCODEC_IDENT of the
+                              ffmpeg build the reference links on x86-64 (lib/ffmpeg/x86_64_shared) */
+    int profile;           /* non-zero: bracket every kernel with CUDA events (see h2j_slot_kernel_ms) */
+} h2j_settings;
+
+typedef struct h2j_encoder h2j_encoder;
+
+/* Fill a settings struct with defaults (1080p, batch 16, 2 slots, reference behaviour). */
+void h2j_default_settings(h2j_settings *s);
+
+int h2j_create(const h2j_settings *s, h2j_encoder **out);
+void h2j_destroy(h2j_encoder *e);
+const char *h2j_last_error(const h2j_encoder *e); /* e may be NULL: error of the last failed h2j_create */
+const char *h2j_status_string(int status);
+int h2j_abi_version(void);
+
+/*
+ * One frame, host planes in, JPEG bytes out, synchronous — the drop-in for
+ * Encoder::yuv2Jpeg() (reference src/Encoder.cpp:89).  planes/strides follow AVFrame.data/.linesize for
+ * an 8-bit 4:2:0 planar frame: plane 0 is width x height, planes 1/2 are ceil(width/2) x ceil(height/2).
+ * Uses slot 0; the planes are staged through pinned memory and copied asynchronously.
+ */
+int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height,
+                     uint8_t *out, size_t out_capacity, size_t *out_size);
+
+/*
+ * Batches.  Frames are same-sized, tightly packed I420: Y (w*h), U (cw*ch), V (cw*ch) with
+ * cw = ceil(w/2), ch = ceil(h/2); consecutive frames are frame_stride bytes apart.
+ *
+ * h2j_submit_host:   frames live in HOST memory (pinned for full PCIe speed); the copy to the device, the
+ *                    kernels and nothing else are enqueued on the slot's stream.  Returns immediately.
+ * h2j_submit_device: frames already live in device memory on the encoder's device.
+ * h2j_collect:       waits for the slot, copies the JPEGs back packed one after another into `out`
+ *                    (offsets[i] .. offsets[i+1]) and frees the slot.  offsets has n+1 entries.
+ * h2j_collect_device:waits for the slot and only reports where the JPEGs are on the device: frame i is
+ *                    at (*d_out) + i * (*d_frame_capacity), sizes[i] bytes long (sizes is a host array).
+ *                    The memory stays valid until the slot is submitted to again.
+ * status[i] (optional, may be NULL) receives a per-frame h2j_status.
+ */
+int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t frame_stride, int n, int width,
+                    int height);
+int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int n, int width,
+                      int height);
+int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, size_t *offsets, int *status);
+int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *d_frame_capacity, size_t *sizes,
+                       int *status);
+/* Block until the slot's stream is idle without collecting (timing helper). */
+int h2j_wait(h2j_encoder *e, int slot);
+
+/* Pinned host memory helpers so callers in any language can get full-speed copies. */
+void *h2j_alloc_pinned(size_t bytes);
+void h2j_free_pinned(void *p);
+
+/*
+ * Standalone plane conversion (kernel 1 on its own): yuv420p limited -> yuvj420p full, with the encoder's
+ * edge replication to whole 16x16 MCUs.  Host in, host out.  out planes are padded:
+ * luma (mcu_w*16) x (mcu_h*16), chroma (mcu_w*8) x (mcu_h*8); pass range_mode to choose the mapping.
+ */
+int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height,
+                    int range_mode, uint8_t *out_y, uint8_t *out_u, uint8_t *out_v);
+
+/* ---- inspection (parity tests read the intermediate products through these) ---------------------- */
+typedef struct h2j_frame_info {
+    int qscale;              /* what the rate control chose */
+    int64_t mb_var_sum;      /* its input */
+    int mcu_w, mcu_h;
+    int header_bytes;        /* SOI .. end of SOS */
+    int64_t scan_bits;       /* entropy-coded bits before padding/stuffing */
+    int64_t stuffed_ff;      /* number of 0x00 bytes inserted */
+    uint8_t intra_matrix[64];/* raster order */
+    uint32_t hist[4][256];   /* DC luma, DC chroma, AC luma, AC chroma symbol counts */
+    uint8_t bits[4][17];     /* DHT BITS (index 1..16) */
+    uint8_t vals[4][256];    /* DHT HUFFVAL */
+    int nvals[4];
+} h2j_frame_info;
+
+/* Valid after h2j_wait/h2j_collect* on the slot and before the next submit to it. */
+int h2j_debug_frame_info(h2j_encoder *e, int slot, int frame, h2j_frame_info *info);
+/* Quantised levels of one frame: mcu_w*mcu_h*6 blocks in MCU order (Y0 Y1 Y2 Y3 Cb Cr), 64 int16 each in
+ * zigzag order (index 0 = quantised DC level, not the difference). */
+int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, size_t out_elems);
+
+/* With settings.profile != 0: milliseconds each kernel of the slot's last batch took, measured with CUDA
+ * events on the stream the kernels were launched on.  names/ms have `cap` entries; returns the count. */
+int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, int cap);
+/* Milliseconds between the first and the last event of the slot's last batch (includes copies). */
+int h2j_slot_total_ms(h2j_encoder *e, int slot, float *ms);
+/* Number of kernel launches issued by this encoder so far. */
+long long h2j_kernel_launches(const h2j_encoder *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2J_B200_H */

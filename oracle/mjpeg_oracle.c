@@ -313,8 +313,10 @@ int orc_rate_control_qscale(int64_t mb_var_sum, int64_t pts, int *lambda_out)
     else if (qm > qmax) qm = qmax;
     q = qm;
 
-    /* back in ff_rate_estimate_qscale: q = av_clip(q, qmin, qmax) goes through int */
-    q = clipi((int)q, qmin, qmax);
+    /* back in ff_rate_estimate_qscale: clip again, then (no adaptive quant) q = (int)(q + 0.5) */
+    if (q < qmin) q = qmin;
+    else if (q > qmax) q = qmax;
+    q = (int)(q + 0.5);
 
     /* estimate_qp(): int quality = q;  update_qscale() */
     int lambda = (int)q;
