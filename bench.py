@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — JPEG encodes/s of the B200 YUV->JPEG path on synthetic textured 1080p frames.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's ffmpeg-mjpeg CPU path on the host cores
+
+A step is one pass of the hot path over one batch of `--frames` distinct frames (default 256 x 1080p = 796 MB
+of input, larger than the 126 MB L2, so nothing is served from cache between steps).
+  value : frames/s, whole job, inputs already resident in HBM (h2j_submit_device), CUDA-event timed.
+  e2e   : frames/s through the public C ABI with HOST buffers: pinned I420 frames in (H2D every step), JPEG
+          bytes out to pinned host memory (D2H every step), wall-clock between device synchronisations.
+  roofline : the dominant kernel's algorithmic bytes / its CUDA-event duration, against MEASURED_PEAKS.json.
+  cpu_baseline : the compiled reference (oracle/_ref, the reference's own Encoder.cpp + vendored libavcodec)
+          timed on this box's host cores on a bounded sample of the same frames.
+Frames shard across ranks with no collective (images are independent): scaling is "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "h264-h265-to-jpeg_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "jpeg_encodes_per_sec_1080p"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--sub-batch", type=int, default=64, help="frames per submitted batch")
+    ap.add_argument("--slots", type=int, default=4, help="batches in flight (streams)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic workload: textured frames (smooth gradients + band-limited texture + mild noise), made on the GPU
+# ------------------------------------------------------------------------------------------------------
+def make_frames_torch(n, w, h, device, seed0=0):
+    import torch
+
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    fb = w * h + 2 * cw * ch
+    stride = (fb + 255) // 256 * 256
+    out = torch.zeros((n, stride), dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+
+    def plane(hh, ww, amp, seed):
+        yy = torch.arange(hh, device=device, dtype=torch.float32)[:, None]
+        xx = torch.arange(ww, device=device, dtype=torch.float32)[None, :]
+        s = float(seed % 97)
+        p = 128 + 50 * torch.sin(xx / 97.0 + s) * torch.cos(yy / 61.0 - s) + amp * torch.sin(xx / 3.1 + yy / 4.3 + s) * torch.sin(yy / 2.3 + 0.37 * s)
+        g.manual_seed(seed)
+        p = p + torch.randn((hh, ww), device=device, generator=g) * (amp / 6.0)
+        return p.clamp(0, 255).to(torch.uint8)
+
+    for i in range(n):
+        seed = seed0 + i
+        amp = 20 + (seed * 7) % 40  # varies the rate-control outcome from frame to frame
+        out[i, : w * h] = plane(h, w, amp, 3 * seed).reshape(-1)
+        out[i, w * h: w * h + cw * ch] = plane(ch, cw, amp // 2, 3 * seed + 1).reshape(-1)
+        out[i, w * h + cw * ch: fb] = plane(ch, cw, amp // 2, 3 * seed + 2).reshape(-1)
+    return out, fb, stride
+
+
+def make_frames_numpy(n, w, h, seed0=0):
+    from tests.support import oracle as orc
+
+    base = [orc.pack_i420(*orc.synth_planes(w, h, "textured", seed=seed0 + s, amp=20 + (s * 7) % 40)) for s in range(min(n, 8))]
+    return np.stack([base[i % len(base)] for i in range(n)])
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------------
+def reference_lib():
+    from tests.support import oracle as orc
+
+    if not orc.have_reference():
+        return None
+    lib = orc.reference()
+    lib.ref_yuv2jpeg_batch_mt.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    return lib
+
+
+def cpu_encode_sample(frames: np.ndarray, w, h, n, threads):
+    """Encode n frames (cycling over `frames`) on `threads` host threads; returns (seconds, kind)."""
+    from tests.support import oracle as orc
+
+    reps = (n + frames.shape[0] - 1) // frames.shape[0]
+    sample = np.ascontiguousarray(np.concatenate([frames] * reps)[:n])
+    sizes = np.zeros(n, np.int64)
+    ref = reference_lib()
+    if ref is not None:
+        t0 = time.perf_counter()
+        ok = ref.ref_yuv2jpeg_batch_mt(sample.ctypes.data, sample.shape[1], n, w, h, sizes.ctypes.data, threads)
+        dt = time.perf_counter() - t0
+        assert ok == n, f"reference encoded {ok}/{n} frames"
+        return dt, "reference", sizes
+    lib = orc.oracle()
+    p = orc.Params(w, h, orc.NOPTS, 0, 0, None)
+    cap = 4 * 1024 * 1024
+    out = np.empty(cap * min(n, 64), np.uint8)
+    t0 = time.perf_counter()
+    done = 0
+    while done < n:
+        m = min(64, n - done)
+        lib.orc_encode_batch_mt(sample[done:].ctypes.data, sample.shape[1], m, C.byref(p), out.ctypes.data, cap, sizes[done:].ctypes.data, threads)
+        done += m
+    return time.perf_counter() - t0, "port", sizes
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    w, h = a.width, a.height
+    cores = os.cpu_count() or 1
+    frames = make_frames_numpy(8, w, h)
+    # bounded sample per step: about 2 frames per core so that warmup+steps finish within minutes
+    n = a.cpu_frames or max(2 * cores, 16)
+    for _ in range(a.warmup):
+        cpu_encode_sample(frames, w, h, max(cores, 8), cores)
+    times = []
+    kind = "port"
+    for _ in range(a.steps):
+        dt, kind, _ = cpu_encode_sample(frames, w, h, n, cores)
+        times.append(dt)
+    total = sum(times)
+    value = n * a.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1000 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16",
+        "data": "synthetic", "mpixel_per_s": value * w * h / 1e6,
+        "config": {"workload": f"{n} synthetic textured {w}x{h} yuv420p frames per step through the reference's Encoder::yuv2Jpeg "
+                               f"(ffmpeg mjpeg, libavcodec 58.117.101) on {cores} host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{n} frames x {a.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import h2j_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the h2j_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, h = a.width, a.height
+    F, SB, NS = a.frames, a.sub_batch, a.slots
+    assert F % SB == 0
+    nsub = F // SB
+    d_frames, fb, stride = make_frames_torch(F, w, h, dev, seed0=rank * F)
+    torch.cuda.synchronize()
+
+    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=SB, n_slots=NS, device=local_rank, profile=True)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    for s_i, st in enumerate(streams):
+        enc.set_stream(s_i, st.cuda_stream)
+    main = torch.cuda.current_stream(dev)
+
+    kernel_ms = {}
+    kernel_calls = {}
+
+    def harvest(slot):
+        for name, ms in enc.kernel_ms(slot):
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
+            kernel_calls[name] = kernel_calls.get(name, 0) + 1
+
+    sizes_total = [0]
+
+    def device_step(record=False):
+        inflight = []
+        for i in range(nsub):
+            slot = i % NS
+            if len(inflight) == NS:
+                s0 = inflight.pop(0)
+                _, _, sizes, st = enc.collect_device(s0)
+                if record:
+                    harvest(s0)
+                    sizes_total[0] += int(sizes.sum())
+            enc.submit_device(slot, d_frames.data_ptr() + i * SB * stride, stride, SB, w, h)
+            inflight.append(slot)
+        for s0 in inflight:
+            _, _, sizes, st = enc.collect_device(s0)
+            if record:
+                harvest(s0)
+                sizes_total[0] += int(sizes.sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity spot check against the oracle (outside every timed region) ---------------------------
+    from tests.support import oracle as orc
+
+    parity = None
+    try:
+        host2 = d_frames[:2].cpu().numpy()
+        enc.submit_device(0, d_frames.data_ptr(), stride, 2, w, h)
+        res = enc.collect(0)
+        ok = True
+        for i in range(2):
+            y, u, v = h2j_b200.split_planes(host2[i], w, h)
+            want, _, _ = orc.oracle_encode(np.ascontiguousarray(y), np.ascontiguousarray(u), np.ascontiguousarray(v))
+            ok = ok and (res.jpegs[i] == want)
+        parity = bool(ok)
+    except Exception as ex:  # the bench still reports; the tests are the gate
+        parity = f"not checked: {ex}"
+
+    # ---- value: device-resident -------------------------------------------------------------------
+    for _ in range(a.warmup):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = enc.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(main)
+    for st in streams:
+        st.wait_stream(main)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        device_step(record=True)
+    for st in streams:
+        main.wait_stream(st)
+    ev1.record(main)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    launches = enc.kernel_launches - launches0
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    value = world * F * a.steps / (dev_ms_max / 1000.0)
+
+    # ---- e2e: pinned host in, pinned host out ------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        h_in = h2j_b200.PinnedBuffer(F * stride)
+        h_in.array[:] = d_frames.reshape(-1).cpu().numpy()
+        out_cap = SB * 2 * 1024 * 1024
+        h_out = [h2j_b200.PinnedBuffer(out_cap) for _ in range(NS)]
+        d2h = [0]
+
+        def e2e_step():
+            inflight = []
+            for i in range(nsub):
+                slot = i % NS
+                if len(inflight) == NS:
+                    s0 = inflight.pop(0)
+                    offs, st = enc.collect_into(s0, h_out[s0].ptr, out_cap)
+                    d2h[0] += int(offs[-1])
+                enc.submit_host(slot, h_in.ptr + i * SB * stride, stride, SB, w, h)
+                inflight.append(slot)
+            for s0 in inflight:
+                offs, st = enc.collect_into(s0, h_out[s0].ptr, out_cap)
+                d2h[0] += int(offs[-1])
+
+        for _ in range(a.warmup):
+            e2e_step()
+        barrier()
+        d2h[0] = 0
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_max = float(t.item())
+        e2e = {"value": world * F * a.steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": world * F * fb,
+               "d2h_bytes_per_step": world * d2h[0] // a.steps, "timing": "wall clock between device synchronisations, max over ranks"}
+        h_in.free()
+        for b in h_out:
+            b.free()
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    mcu = ((w + 15) // 16) * ((h + 15) // 16)
+    nblk = mcu * 6
+    avg_jpeg = sizes_total[0] / max(1, F * a.steps)
+    alg_bytes = {  # per frame; DESIGN.md section 5
+        "mbvar_kernel": w * h,
+        "fdct_quant_kernel": fb + nblk * (128 + 8 + 2),
+        "entropy_kernel": nblk * (128 + 8 + 2) + avg_jpeg,
+        "stuff_kernel": 2 * avg_jpeg,
+        "huffman_kernel": nblk * 2,
+    }
+    per_kernel = {}
+    for name, ms in kernel_ms.items():
+        calls = kernel_calls[name]
+        avg_ms = ms / calls
+        entry = {"avg_ms": avg_ms, "launches": calls}
+        if name in alg_bytes:
+            entry["gbs"] = alg_bytes[name] * SB / (avg_ms * 1e-3) / 1e9
+        per_kernel[name] = entry
+    dom = max((k for k in per_kernel if k in ("fdct_quant_kernel", "entropy_kernel", "mbvar_kernel", "stuff_kernel")),
+              key=lambda k: per_kernel[k]["avg_ms"])
+    roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": per_kernel[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes[dom] * SB,
+            "note": "per-kernel CUDA events on the launching stream inside the timed region; with several slots in flight a bracket "
+                    "can include a neighbour stream's kernels, so this is a lower bound on the kernel's own rate"}
+    for k in ("fdct_quant_kernel", "mbvar_kernel", "entropy_kernel"):
+        if k in per_kernel and "gbs" in per_kernel[k]:
+            roof[k + "_frac"] = per_kernel[k]["gbs"] / peak
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = a.cpu_frames or max(4 * cores, 32)
+        host8 = d_frames[:8, :fb].cpu().numpy()
+        cpu_encode_sample(host8, w, h, min(n, 2 * cores), cores)  # warm
+        dt, kind, _ = cpu_encode_sample(host8, w, h, n, cores)
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{n} of the bench frames, {cores} host threads, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int16", "data": "synthetic",
+            "mpixel_per_s": value * w * h / 1e6,
+            "config": {"workload": f"{F} distinct synthetic textured {w}x{h} yuv420p frames per GPU per step (configs[2] shape), "
+                                   f"sub-batches of {SB} on {NS} streams, bit-exact ffmpeg-mjpeg output",
+                       "frames_per_step_per_gpu": F, "sub_batch": SB, "slots": NS,
+                       "l2_policy": f"inputs larger than L2: {F * fb / 1e6:.0f} MB of frames + {F * nblk * 128 / 1e6:.0f} MB of coefficients per step",
+                       "avg_jpeg_bytes": avg_jpeg, "parity_spot_check_vs_oracle": parity},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_ms_per_step": 1000 * wall / a.steps,
+            "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

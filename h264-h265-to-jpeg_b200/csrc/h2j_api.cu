@@ -49,6 +49,8 @@ struct Slot {
     uint8_t *h_stage = nullptr;               // pinned staging for h2j_encode_frame / convert
     size_t h_stage_bytes = 0;
     bool busy = false;
+    bool own_stream = true;
+    bool packed = false;      // pack_kernel already ran for the batch in flight
     int n = 0;
     FrameLayout L{};
     std::vector<KernelTiming> timings;
@@ -192,7 +194,9 @@ struct ScopedTiming {
 };
 
 // Enqueue the whole pipeline for `n` frames at `d_frames` on the slot's stream.
-int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n)
+int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack);
+
+int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bool pack)
 {
     const FrameLayout &L = sl.L;
     cudaStream_t st = sl.stream;
@@ -236,7 +240,9 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n)
         e->launches++;
     }
     CU(e, cudaGetLastError());
-    return H2J_OK;
+    // sizes/status (and, for host consumers, the packed payload) are produced inside the same enqueue so that
+    // collecting a batch costs no further kernel launches
+    return enqueue_pack_and_sizes(e, sl, pack);
 }
 
 int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
@@ -247,6 +253,7 @@ int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
         pack_offsets_kernel<<<1, 32, 0, st>>>(sl.d_tabs, sl.n, (long long)e->out_cap, sl.d_offsets, sl.d_status);
         e->launches++;
     }
+    sl.packed = pack;
     if (pack) {
         ScopedTiming t(e, sl, "pack_kernel");
         pack_kernel<<<dim3(8, sl.n), 256, 0, st>>>(sl.d_out, (long long)e->out_cap, sl.d_offsets, sl.d_packed);
@@ -254,6 +261,7 @@ int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
     }
     CU(e, cudaMemcpyAsync(sl.h_offsets, sl.d_offsets, sizeof(unsigned long long) * (sl.n + 1), cudaMemcpyDeviceToHost, st));
     CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int) * sl.n, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaEventRecord(sl.ev_done, st));
     CU(e, cudaGetLastError());
     return H2J_OK;
 }
@@ -277,7 +285,7 @@ void free_slot(Slot &sl)
     for (auto &t : sl.timings) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
     if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
-    if (sl.stream) cudaStreamDestroy(sl.stream);
+    if (sl.stream && sl.own_stream) cudaStreamDestroy(sl.stream);
     sl = Slot{};
 }
 
@@ -444,7 +452,7 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     if (rc) return rc;
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
-    rc = launch_pipeline(e, sl, d_frames, n);
+    rc = launch_pipeline(e, sl, d_frames, n, false);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -469,9 +477,23 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     if (frame_stride == dstride) CU(e, cudaMemcpyAsync(sl.d_frames, frames, dstride * (n - 1) + fb, cudaMemcpyHostToDevice, sl.stream));
     else CU(e, cudaMemcpy2DAsync(sl.d_frames, dstride, frames, frame_stride, fb, n, cudaMemcpyHostToDevice, sl.stream));
-    rc = launch_pipeline(e, sl, sl.d_frames, n);
+    rc = launch_pipeline(e, sl, sl.d_frames, n, true);
     if (rc) return rc;
     sl.busy = true;
+    return H2J_OK;
+}
+
+int h2j_slot_set_stream(h2j_encoder *e, int slot, void *cuda_stream)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
+    CU(e, cudaSetDevice(e->s.device));
+    CU(e, cudaStreamSynchronize(sl.stream));
+    if (sl.own_stream) CU(e, cudaStreamDestroy(sl.stream));
+    sl.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    sl.own_stream = false;
     return H2J_OK;
 }
 
@@ -491,8 +513,12 @@ int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, siz
     if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
     if (!out || !offsets) return fail(e, H2J_ERR_INVALID_ARG, "null out/offsets");
     CU(e, cudaSetDevice(e->s.device));
-    rc = enqueue_pack_and_sizes(e, sl, true);
-    if (rc) { sl.busy = false; return rc; }
+    if (!sl.packed) {  // submitted with h2j_submit_device: pack now
+        ScopedTiming t(e, sl, "pack_kernel");
+        pack_kernel<<<dim3(8, sl.n), 256, 0, sl.stream>>>(sl.d_out, (long long)e->out_cap, sl.d_offsets, sl.d_packed);
+        e->launches++;
+        sl.packed = true;
+    }
     CU(e, cudaStreamSynchronize(sl.stream));
     sl.busy = false;
     const size_t total = (size_t)sl.h_offsets[sl.n];
@@ -517,9 +543,6 @@ int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *
     Slot &sl = e->slots[slot];
     if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
     CU(e, cudaSetDevice(e->s.device));
-    rc = enqueue_pack_and_sizes(e, sl, false);
-    if (rc) { sl.busy = false; return rc; }
-    CU(e, cudaEventRecord(sl.ev_done, sl.stream));
     CU(e, cudaStreamSynchronize(sl.stream));
     sl.busy = false;
     int worst = H2J_OK;

@@ -73,7 +73,7 @@ EXPORTS = [
     "h2j_default_settings", "h2j_create", "h2j_destroy", "h2j_last_error", "h2j_status_string", "h2j_abi_version",
     "h2j_encode_frame", "h2j_submit_host", "h2j_submit_device", "h2j_collect", "h2j_collect_device", "h2j_wait",
     "h2j_alloc_pinned", "h2j_free_pinned", "h2j_convert_pad", "h2j_debug_frame_info", "h2j_debug_coefficients",
-    "h2j_slot_kernel_ms", "h2j_slot_total_ms", "h2j_kernel_launches",
+    "h2j_slot_kernel_ms", "h2j_slot_total_ms", "h2j_kernel_launches", "h2j_slot_set_stream",
 ]
 
 _lib = None
@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
     lib.h2j_collect.argtypes = [vp, ci, vp, sz, C.POINTER(sz), C.POINTER(ci)]
     lib.h2j_collect_device.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
     lib.h2j_wait.argtypes = [vp, ci]
+    lib.h2j_slot_set_stream.argtypes = [vp, ci, vp]
     lib.h2j_alloc_pinned.argtypes = [sz]
     lib.h2j_alloc_pinned.restype = vp
     lib.h2j_free_pinned.argtypes = [vp]
@@ -234,6 +235,10 @@ class Encoder:
     def submit_device(self, slot: int, d_frames_ptr: int, frame_stride: int, n: int, width: int, height: int) -> None:
         self._check(self._lib.h2j_submit_device(self._h, slot, d_frames_ptr, frame_stride, n, width, height))
         self._n_in_slot[slot] = n
+
+    def set_stream(self, slot: int, cuda_stream: int) -> None:
+        """Enqueue the slot's work on a caller-owned stream (raw cudaStream_t handle)."""
+        self._check(self._lib.h2j_slot_set_stream(self._h, slot, cuda_stream))
 
     def wait(self, slot: int) -> None:
         self._check(self._lib.h2j_wait(self._h, slot))

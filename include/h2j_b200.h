@@ -106,6 +106,9 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
 int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, size_t *offsets, int *status);
 int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *d_frame_capacity, size_t *sizes,
                        int *status);
+/* Make the slot enqueue on a caller-owned CUDA stream (a cudaStream_t, e.g. torch.cuda.Stream().cuda_stream)
+ * instead of its own, so the caller can bracket the work with its own events.  The slot must be idle. */
+int h2j_slot_set_stream(h2j_encoder *e, int slot, void *cuda_stream);
 /* Block until the slot's stream is idle without collecting (timing helper). */
 int h2j_wait(h2j_encoder *e, int slot);
 

@@ -850,3 +850,126 @@ int orc_encode_batch_mt(const uint8_t *frames, long frame_stride, int n, const o
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Independent check: baseline JPEG entropy DECODER (ITU T.81 F.2.2), used by the round-trip tests   */
+/* to recover the quantised levels from a finished JPEG without going through any encoder code.      */
+/* out: levels in zigzag order per block, MCU order Y0 Y1 Y2 Y3 Cb Cr (DC as level, not difference).  */
+/* Returns the number of blocks decoded, or a negative error.  info = {w, h, n_ff00, scan_bytes}.     */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { int mincode[18], maxcode[18], valptr[18]; uint8_t vals[256]; int present; } dec_tab_t;
+typedef struct { const uint8_t *p, *end; uint32_t acc; int n; long ff00; int hit_marker; } dec_bits_t;
+
+static int dec_bit(dec_bits_t *b)
+{
+    if (b->n == 0) {
+        if (b->p >= b->end) return -1;
+        uint8_t c = *b->p++;
+        if (c == 0xff) {
+            if (b->p < b->end && *b->p == 0x00) { b->p++; b->ff00++; }
+            else { b->hit_marker = 1; return -1; }
+        }
+        b->acc = c;
+        b->n = 8;
+    }
+    b->n--;
+    return (b->acc >> b->n) & 1;
+}
+static int dec_sym(dec_bits_t *b, const dec_tab_t *t)
+{
+    int code = 0;
+    for (int l = 1; l <= 16; l++) {
+        int bit = dec_bit(b);
+        if (bit < 0) return -1;
+        code = (code << 1) | bit;
+        if (t->maxcode[l] >= 0 && code <= t->maxcode[l] && code >= t->mincode[l]) return t->vals[t->valptr[l] + code - t->mincode[l]];
+    }
+    return -2;
+}
+static int dec_receive_extend(dec_bits_t *b, int s)
+{
+    int v = 0;
+    for (int i = 0; i < s; i++) { int bit = dec_bit(b); if (bit < 0) return 0x7fffffff; v = (v << 1) | bit; }
+    if (s && v < (1 << (s - 1))) v -= (1 << s) - 1;
+    return v;
+}
+
+long orc_jpeg_decode_coefs(const uint8_t *jpeg, long n, int16_t *out, long cap_blocks, long *info)
+{
+    dec_tab_t tabs[2][2];
+    memset(tabs, 0, sizeof tabs);
+    long i = 2;
+    int w = 0, h = 0;
+    if (n < 4 || jpeg[0] != 0xff || jpeg[1] != 0xd8) return -1;
+    while (i + 4 <= n) {
+        if (jpeg[i] != 0xff) return -2;
+        int m = jpeg[i + 1];
+        long L = (jpeg[i + 2] << 8) | jpeg[i + 3];
+        const uint8_t *seg = jpeg + i + 4;
+        if (m == 0xc4) {
+            long k = 0;
+            while (k < L - 2) {
+                int tc = seg[k] >> 4, th = seg[k] & 15;
+                if (tc > 1 || th > 1) return -3;
+                dec_tab_t *t = &tabs[tc][th];
+                const uint8_t *bits = seg + k + 1;
+                int total = 0, code = 0;
+                for (int l = 1; l <= 16; l++) {
+                    t->valptr[l] = total;
+                    t->mincode[l] = code;
+                    total += bits[l - 1];
+                    code += bits[l - 1];
+                    t->maxcode[l] = bits[l - 1] ? code - 1 : -1;
+                    code <<= 1;
+                }
+                memcpy(t->vals, seg + k + 17, total);
+                t->present = 1;
+                k += 17 + total;
+            }
+        } else if (m == 0xc0) {
+            h = (seg[1] << 8) | seg[2];
+            w = (seg[3] << 8) | seg[4];
+            if (seg[5] != 3 || seg[7] != 0x22 || seg[10] != 0x11 || seg[13] != 0x11) return -4;
+        } else if (m == 0xda) {
+            i += 2 + L;
+            break;
+        }
+        i += 2 + L;
+    }
+    if (!w || !h) return -5;
+    const int mbw = (w + 15) >> 4, mbh = (h + 15) >> 4;
+    const long nblk = (long)mbw * mbh * 6;
+    if (nblk > cap_blocks) return -6;
+    dec_bits_t b = {jpeg + i, jpeg + n, 0, 0, 0, 0};
+    int pred[3] = {128, 128, 128}; /* the encoder's last_dc starts at 128 (level shift folded into DC) */
+    for (long blk = 0; blk < nblk; blk++) {
+        const int nn = (int)(blk % 6), comp = nn < 4 ? 0 : nn - 3, th = nn < 4 ? 0 : 1;
+        int16_t *o = out + blk * 64;
+        memset(o, 0, 128);
+        int s = dec_sym(&b, &tabs[0][th]);
+        if (s < 0) return -7;
+        int diff = dec_receive_extend(&b, s);
+        if (diff == 0x7fffffff) return -8;
+        pred[comp] += diff;
+        o[0] = (int16_t)pred[comp];
+        for (int k = 1; k < 64;) {
+            int rs = dec_sym(&b, &tabs[1][th]);
+            if (rs < 0) return -9;
+            int r = rs >> 4, sz = rs & 15;
+            if (sz == 0) {
+                if (r == 15) { k += 16; continue; }
+                break; /* EOB */
+            }
+            k += r;
+            if (k > 63) return -10;
+            int v = dec_receive_extend(&b, sz);
+            if (v == 0x7fffffff) return -11;
+            o[k++] = (int16_t)v;
+        }
+    }
+    /* remaining bits must be 1-padding, then EOI */
+    while (b.n > 0) { if (dec_bit(&b) != 1) return -12; }
+    if (b.p + 2 > b.end || b.p[0] != 0xff || b.p[1] != 0xd9) return -13;
+    if (info) { info[0] = w; info[1] = h; info[2] = b.ff00; info[3] = (long)(b.p - (jpeg + i)); }
+    return nblk;
+}

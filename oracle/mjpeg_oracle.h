@@ -60,6 +60,10 @@ void orc_range_chroma(const uint8_t *src, int sstride, uint8_t *dst, int dstride
 long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
                       const orc_params *p, uint8_t *out, long cap, orc_debug *dbg);
 
+/* Baseline JPEG entropy decoder (independent of the encoder restatement): quantised levels back out of a
+ * finished JPEG, zigzag order, MCU order.  Returns blocks decoded or <0.  info = {w, h, n_ff00, scan_bytes}. */
+long orc_jpeg_decode_coefs(const uint8_t *jpeg, long n, int16_t *out, long cap_blocks, long *info);
+
 /* N same-sized frames laid out back to back (frame stride in bytes given), T threads.
  * out: cap_per_frame bytes per frame; sizes[i] receives each size.  Returns 0 on success. */
 int orc_encode_batch_mt(const uint8_t *frames, long frame_stride, int n, const orc_params *p,

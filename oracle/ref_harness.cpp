@@ -193,6 +193,59 @@ int ref_sws_limited_to_full(const uint8_t *y, const uint8_t *u, const uint8_t *v
     return r == h ? 1 : 0;
 }
 
+// N same-sized tight I420 frames (frame_stride bytes apart), `threads` host threads, each thread running the
+// reference's Encoder::yuv2Jpeg on frames tid, tid+threads, ... — one fresh Encoder per frame, exactly as
+// reference src/Decoder.cpp:319 does — writing to tmpfs.  sizes[i] receives each JPEG's size (0 on failure).
+// Returns the number of frames that encoded.
+}  // extern "C"
+#include <pthread.h>
+#include <sys/stat.h>
+namespace {
+struct MtJob {
+    const uint8_t *frames; long stride; int n, w, h, tid, nthreads; long *sizes; int ok;
+};
+void *mt_worker(void *arg)
+{
+    MtJob *j = static_cast<MtJob *>(arg);
+    const int w = j->w, h = j->h, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    char path[128];
+    snprintf(path, sizeof path, "/dev/shm/h2j_refmt_%d_%d.jpg", (int)getpid(), j->tid);
+    for (int i = j->tid; i < j->n; i += j->nthreads) {
+        const uint8_t *y = j->frames + (long)i * j->stride;
+        const uint8_t *u = y + (long)w * h, *v = u + (long)cw * ch;
+        AVFrame *f = make_frame(y, w, u, cw, v, cw, w, h, AV_NOPTS_VALUE, AV_PIX_FMT_YUV420P);
+        if (!f) continue;
+        const bool ok = Encoder(path).yuv2Jpeg(f);
+        av_frame_free(&f);
+        long sz = 0;
+        if (ok) {
+            struct stat st;
+            if (stat(path, &st) == 0) sz = (long)st.st_size;
+            j->ok++;
+        }
+        if (j->sizes) j->sizes[i] = sz;
+    }
+    unlink(path);
+    return nullptr;
+}
+}  // namespace
+extern "C" {
+int ref_yuv2jpeg_batch_mt(const uint8_t *frames, long frame_stride, int n, int w, int h, long *sizes, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 512) threads = 512;
+    StdoutSilencer s(true);
+    pthread_t th[512];
+    MtJob jobs[512];
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = MtJob{frames, frame_stride, n, w, h, t, threads, sizes, 0};
+        pthread_create(&th[t], nullptr, mt_worker, &jobs[t]);
+    }
+    int ok = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], nullptr); ok += jobs[t].ok; }
+    return ok;
+}
+
 const char *ref_version(void) { return LIBAVCODEC_IDENT; }
 
 }  // extern "C"

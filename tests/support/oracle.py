@@ -145,3 +145,38 @@ def synth_planes(w, h, kind="textured", seed=0, amp=40):
 
 def pack_i420(y, u, v) -> np.ndarray:
     return np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)])
+
+
+def golden_planes(w, h, seed, amp):
+    """Integer-only deterministic frame generator for the committed golden vectors (no floating point, so the
+    planes are bit-identical on every platform): random 8x8-block means + random walk texture, clipped."""
+    rng = np.random.default_rng(seed)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+
+    def plane(hh, ww, a):
+        blocks = rng.integers(32, 224, ((hh + 7) // 8, (ww + 7) // 8), dtype=np.int64)
+        base = np.kron(blocks, np.ones((8, 8), dtype=np.int64))[:hh, :ww]
+        walk = np.cumsum(rng.integers(-a, a + 1, (hh, ww), dtype=np.int64), axis=1) // 4
+        tex = rng.integers(-a, a + 1, (hh, ww), dtype=np.int64)
+        return np.clip(base + walk + tex, 0, 255).astype(np.uint8)
+
+    return plane(h, w, amp), plane(ch, cw, max(1, amp // 2)), plane(ch, cw, max(1, amp // 2))
+
+
+def decode_coefs(jpeg: bytes):
+    """Independent baseline entropy decode (oracle/mjpeg_oracle.c orc_jpeg_decode_coefs).
+    Returns (levels[n_blocks, 64] zigzag, info = [w, h, n_ff00, scan_bytes])."""
+    lib = oracle()
+    lib.orc_jpeg_decode_coefs.restype = C.c_long
+    lib.orc_jpeg_decode_coefs.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+    jb = np.frombuffer(jpeg, np.uint8)
+    # geometry from SOF0
+    i = jpeg.find(b"\xff\xc0")
+    h = (jpeg[i + 5] << 8) | jpeg[i + 6]
+    w = (jpeg[i + 7] << 8) | jpeg[i + 8]
+    nblk = ((w + 15) // 16) * ((h + 15) // 16) * 6
+    out = np.zeros((nblk, 64), np.int16)
+    info = np.zeros(4, np.int64)
+    n = lib.orc_jpeg_decode_coefs(jb.ctypes.data, len(jpeg), out.ctypes.data, nblk, info.ctypes.data)
+    assert n == nblk, f"entropy decode failed: {n}"
+    return out, info
