@@ -374,8 +374,8 @@ def run_ours(a):
     avg_jpeg = sizes_total[0] / max(1, F * a.steps)
     alg_bytes = {  # per frame; DESIGN.md section 5
         "mbvar_kernel": w * h,
-        "fdct_quant_kernel": fb + nblk * (128 + 8 + 2),
-        "entropy_kernel": nblk * (128 + 8 + 2) + avg_jpeg,
+        "fdct_quant_kernel": fb + nblk * (132 + 8),
+        "entropy_kernel": nblk * (132 + 8) + avg_jpeg,
         "stuff_kernel": 2 * avg_jpeg,
         "huffman_kernel": nblk * 2,
     }

@@ -29,14 +29,14 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
     uint8_t *d_frames = nullptr;  // staging for host submits
-    int16_t *d_coefs = nullptr;
+    uint32_t *d_images = nullptr;  // [max_batch][images_cap] tile images (h2j_common.cuh)
     unsigned long long *d_masks = nullptr;
-    int16_t *d_dcs = nullptr;
-    uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket — zeroed every batch
+    uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
     unsigned long long *d_descs = nullptr;
     unsigned int *d_ticket = nullptr;
+    unsigned int *d_chunk_ff = nullptr;
     FrameTab *d_tabs = nullptr;
     uint32_t *d_scan = nullptr;
     uint8_t *d_out = nullptr;
@@ -66,8 +66,11 @@ struct h2j_encoder {
     int sm_count = 0;
     size_t out_cap = 0;           // per-frame JPEG capacity (multiple of 16)
     long long scan_cap_words = 0;
-    long long blocks_cap = 0;     // blocks per frame at max geometry, rounded up to whole FDCT tiles
-    int tiles_cap = 0;            // entropy tiles per frame at max geometry
+    long long images_cap = 0;     // K2 tile images per frame at max geometry, rounded up to whole K4 tiles
+    long long blocks_cap = 0;     // images_cap * 96
+    int tiles_cap = 0;            // K4 tiles per frame at max geometry
+    int chunks_cap = 0;           // K5 chunks per frame
+    int stuff_ctas = 32;          // K5 CTAs per frame
     size_t frame_bytes_cap = 0;
     uint8_t *d_qscale_lut = nullptr;
     char *d_comment = nullptr;
@@ -207,36 +210,32 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
         mbvar_kernel<<<dim3(L.mcu_h, n), 128, 0, st>>>(d_frames, L, sl.d_state);
         e->launches++;
     }
-    {
-        ScopedTiming t(e, sl, "frame_setup_kernel");
-        frame_setup_kernel<<<n, 64, 0, st>>>(L, sl.d_state, e->d_qscale_lut, sl.d_tabs);
-        e->launches++;
-    }
+    const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
     {
         ScopedTiming t(e, sl, "fdct_quant_kernel");
-        const int n_tiles = (L.n_mcu + kFdctMcusPerTile - 1) / kFdctMcusPerTile;
         const int tiles_per_cta = 4;
         fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, 0, st>>>(
-            d_frames, L, sl.d_tabs, sl.d_state, sl.d_coefs, sl.d_masks, sl.d_dcs, e->blocks_cap, tiles_per_cta);
+            d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs, sl.d_images, sl.d_masks, e->images_cap, e->blocks_cap, tiles_per_cta);
         e->launches++;
     }
     {
         ScopedTiming t(e, sl, "huffman_kernel");
-        huffman_kernel<<<n, kHuffThreads, 4 * sizeof(HuffScratch), st>>>(L, sl.d_tabs, sl.d_state, sl.d_dcs, e->blocks_cap, sl.d_out,
-                                                                       (long long)e->out_cap, e->d_comment, (int)e->comment.size());
+        huffman_kernel<<<n, kHuffThreads, 4 * sizeof(HuffScratch), st>>>(L, sl.d_tabs, sl.d_state, sl.d_out, (long long)e->out_cap,
+                                                                       e->d_comment, (int)e->comment.size());
         e->launches++;
     }
-    const int tiles_per_frame = (L.n_blocks + kEntropyThreads - 1) / kEntropyThreads;
+    const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
         ScopedTiming t(e, sl, "entropy_kernel");
-        entropy_kernel<<<tiles_per_frame * n, kEntropyThreads, (kEntropyBufWords + 2) * sizeof(unsigned int), st>>>(
-            L, sl.d_tabs, sl.d_state, sl.d_coefs, sl.d_masks, sl.d_dcs, e->blocks_cap, sl.d_descs, sl.d_ticket, tiles_per_frame, sl.d_scan,
-            e->scan_cap_words);
+        entropy_kernel<<<tiles_per_frame * n, kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_state, sl.d_images, e->images_cap, sl.d_masks,
+                                                                               e->blocks_cap, sl.d_descs, sl.d_ticket, tiles_per_frame, sl.d_scan,
+                                                                               e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
         e->launches++;
     }
     {
         ScopedTiming t(e, sl, "stuff_kernel");
-        stuff_kernel<<<n, kStuffThreads, 0, st>>>(sl.d_tabs, sl.d_state, sl.d_scan, e->scan_cap_words, sl.d_out, (long long)e->out_cap);
+        stuff_kernel<<<dim3(e->stuff_ctas, n), kStuffThreads, 0, st>>>(sl.d_tabs, sl.d_state, sl.d_scan, e->scan_cap_words, sl.d_chunk_ff,
+                                                                      e->chunks_cap, sl.d_out, (long long)e->out_cap);
         e->launches++;
     }
     CU(e, cudaGetLastError());
@@ -276,7 +275,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_coefs); cudaFree(sl.d_masks); cudaFree(sl.d_dcs); cudaFree(sl.d_zero);
+    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_masks); cudaFree(sl.d_zero);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -381,8 +380,10 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->scan_cap_words = (long long)(e->out_cap / 4);
     const int mcu_w = (s->max_width + 15) >> 4, mcu_h = (s->max_height + 15) >> 4;
     const long long n_mcu = (long long)mcu_w * mcu_h;
-    e->blocks_cap = (n_mcu + kFdctMcusPerTile - 1) / kFdctMcusPerTile * kFdctThreads;
-    e->tiles_cap = (int)((n_mcu * 6 + kEntropyThreads - 1) / kEntropyThreads);
+    e->images_cap = ((n_mcu + kTileMcus - 1) / kTileMcus + kEntFdctTiles - 1) / kEntFdctTiles * kEntFdctTiles;
+    e->blocks_cap = e->images_cap * kTileBlocks;
+    e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
+    e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
     e->frame_bytes_cap = align_up(tight_frame_bytes(s->max_width, s->max_height), 256);
 
     // constant tables
@@ -398,7 +399,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
     CUB(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
-    CUB(cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kEntropyBufWords + 2) * sizeof(unsigned int))));
+    CUB(cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
 
     const int B = s->max_batch;
     e->slots.resize(s->n_slots);
@@ -407,16 +408,17 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_begin));
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
-        CUB(cudaMalloc(&sl.d_coefs, (size_t)e->blocks_cap * B * 64 * sizeof(int16_t)));
+        CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
         CUB(cudaMalloc(&sl.d_masks, (size_t)e->blocks_cap * B * sizeof(unsigned long long)));
-        CUB(cudaMalloc(&sl.d_dcs, (size_t)e->blocks_cap * B * sizeof(int16_t)));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
         const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->tiles_cap * B, 256);
-        sl.zero_bytes = state_bytes + desc_bytes + 256;
+        const size_t chunk_bytes = align_up(sizeof(unsigned int) * (size_t)e->chunks_cap * B, 256);
+        sl.zero_bytes = state_bytes + desc_bytes + 256 + chunk_bytes;
         CUB(cudaMalloc(&sl.d_zero, sl.zero_bytes));
         sl.d_state = reinterpret_cast<FrameState *>(sl.d_zero);
         sl.d_descs = reinterpret_cast<unsigned long long *>(sl.d_zero + state_bytes);
         sl.d_ticket = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes);
+        sl.d_chunk_ff = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes + 256);
         CUB(cudaMalloc(&sl.d_tabs, sizeof(FrameTab) * B));
         CUB(cudaMalloc(&sl.d_scan, (size_t)e->scan_cap_words * 4 * B));
         CUB(cudaMalloc(&sl.d_out, e->out_cap * B));
@@ -669,7 +671,20 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     if (out_elems < need) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "need %zu int16 elements", need);
     CU(e, cudaSetDevice(e->s.device));
     CU(e, cudaStreamSynchronize(sl.stream));
-    CU(e, cudaMemcpy(out, sl.d_coefs + (size_t)frame * e->blocks_cap * 64, need * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    // tile images -> dense blocks; halfword 0 of a record is the DC difference, so the levels are rebuilt by
+    // running the encoder's predictors (one per component, reset to 128) over the blocks in coding order
+    const int n_tiles = (sl.L.n_mcu + kTileMcus - 1) / kTileMcus;
+    std::vector<int16_t> img((size_t)n_tiles * kTileImageWords * 2);
+    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->images_cap * kTileImageWords, img.size() * sizeof(int16_t),
+                     cudaMemcpyDeviceToHost));
+    int last_dc[3] = {128, 128, 128};
+    for (int b = 0; b < sl.L.n_blocks; b++) {
+        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords * 2 + (size_t)(b % kTileBlocks) * kBlkHalf);
+        const int n = b % 6, comp = n < 4 ? 0 : n - 3;
+        last_dc[comp] += rec[0];
+        out[(size_t)b * 64] = (int16_t)last_dc[comp];
+        for (int k = 1; k < 64; k++) out[(size_t)b * 64 + k] = rec[2 * (k & 31) + (k >> 5)];
+    }
     return H2J_OK;
 }
 

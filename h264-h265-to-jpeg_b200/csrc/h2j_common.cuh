@@ -1,0 +1,125 @@
+// Device side of h2j_b200: the YUV -> JPEG stage of the reference (src/Encoder.cpp:89-297, i.e. libavcodec's
+// mjpeg encoder as the reference configures it) as sm_100a kernels.  One launch handles a batch of same-sized
+// frames; frames never interact, so the batch index is simply a grid dimension.
+//
+//   K1  mbvar_kernel        luma 16x16 variance sums -> rate-control input              (HBM bound, 1 B/px read)
+//   K2  fdct_quant_kernel   qscale + quantiser set-up, (range convert +) edge replicate + FDCT + quantise +
+//                           zigzag + DC prediction + DC/AC symbol histograms           (issue bound)
+//   K3  huffman_kernel      4 optimal (package-merge) tables, code tables, JPEG header
+//   K4  entropy_kernel      per-block bit lengths, decoupled look-back scan over tiles, bit packing, 0xFF census
+//   K5  stuff_kernel        0xFF -> 0xFF00 expansion behind the header, EOI, final size
+//   K6  pack_kernel         optional: JPEGs of a batch packed back to back for one D2H copy
+//   convert_pad_kernel      kernel 1 on its own: range convert + MCU padding to planes (h2j_convert_pad)
+//
+// This header: the layout shared by host and device, constants and small helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "h2j_math.cuh"
+
+namespace h2j {
+
+struct FrameLayout {
+    int w, h;          // luma size
+    int cw, ch;        // chroma size the encoder reads: w>>1, h>>1 (mpegvideo_enc.c load_input_picture)
+    int y_pitch, c_pitch;
+    long long u_off, v_off, frame_stride;  // bytes from the frame base / between frames
+    int mcu_w, mcu_h, n_mcu, n_blocks;
+    int aligned8;      // every row of every plane starts on an 8-byte boundary -> 64-bit loads
+    int aligned16;     // ... 16-byte boundary -> 128-bit loads (mbvar)
+    int range_mode;
+    int fixed_qscale;
+};
+
+// ---- coefficient store ("tile images") -----------------------------------------------------------
+// K2 works on tiles of 16 consecutive MCUs (96 blocks, coding order).  A tile leaves K2 as one contiguous
+// image of 96 block records, 33 words each:
+//   word j (0..31)  low half: level j, high half: level j + 32 of the zigzag scan (this pairing lets K2 derive
+//                   the non-zero mask from packed 16-bit minima); level 0 is stored as the DC *difference* to the
+//                   previous block of the same component, i.e. what gets coded
+//   word 32         padding: makes the record stride odd in words, so that K4's per-thread reads of
+//                   "coefficient k of my block" from the image in shared memory are bank-conflict free
+// K4 pulls two images (192 blocks) into shared memory with one bulk copy.
+constexpr int kTileMcus = 16;
+constexpr int kTileBlocks = kTileMcus * 6;                  // 96
+constexpr int kBlkWords = 33;
+constexpr int kBlkHalf = kBlkWords * 2;                     // 66
+constexpr int kTileImageWords = kTileBlocks * kBlkWords;    // 3168
+constexpr int kTileImageBytes = kTileImageWords * 4;        // 12672 = 792 * 16
+constexpr int kFdctThreads = kTileBlocks;
+
+constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
+constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192
+constexpr int kEntThreads = kEntBlocks;
+constexpr int kEntWinWords = 2048;                          // shared-memory bit window: 8 KiB = 65536 bits
+constexpr int kEntWinBits = kEntWinWords * 32;
+constexpr int kMaxBitsPerBlock = 27 * 64;                   // DC (16+11) + 63 * (16+11); ZRLs only replace coefficients
+
+constexpr int kHuffGroup = 128;                             // threads per table
+constexpr int kHuffThreads = 4 * kHuffGroup;
+constexpr int kStuffThreads = 256;
+constexpr int kChunkShift = 10;                             // K5 works on chunks of 1024 scan words (4 KiB)
+constexpr int kChunkWords = 1 << kChunkShift;
+constexpr int kQscaleLutSize = 65536;
+
+// Per-frame table block written by K2 (quantiser part) and K3 (Huffman part), read by K4/K5.
+struct FrameTab {
+    uint32_t qpack[64];      // raster order: q | (bias*q) << 16   (inspection)
+    uint8_t dqt_zz[64];      // DQT payload (zigzag order)
+    uint8_t intra[64];       // raster order (inspection)
+    uint32_t hcode[4][256];  // (code << 5) | size; classes: 0 DC luma, 1 DC chroma, 2 AC luma, 3 AC chroma
+    uint8_t bits[4][17];
+    uint8_t vals[4][256];
+    int nvals[4];
+    int qscale;
+    int header_bytes;
+    int status;              // h2j_status of this frame
+    int pad_;
+    long long mb_var_sum;
+    long long scan_bits;
+    long long stuffed_ff;
+    long long jpeg_bytes;
+};
+
+// Per-frame state zeroed by one memset at the start of every batch.
+struct FrameState {
+    unsigned long long var_sum;
+    unsigned long long scan_bits;   // written by the frame's last entropy tile
+    unsigned int hist[4][256];      // DC luma, DC chroma, AC luma, AC chroma symbol counts (K2)
+};
+
+__constant__ uint8_t c_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+// ff_mpeg1_default_intra_matrix, raster order
+__constant__ uint8_t c_mpeg1_intra[64] = {8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34,
+                                          34, 38, 22, 22, 26, 27, 29, 34, 37, 40, 22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32,
+                                          35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
+// swscale limited->full LUTs, [0] luma, [1] chroma; filled by the host at create time from the closed form
+__constant__ uint8_t c_range_lut[2][256];
+
+// compile-time zigzag for the register-resident block
+__host__ __device__ constexpr int zz_of(int k)
+{
+    constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[k];
+}
+
+__device__ __forceinline__ uint2 ldg64(const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// JPEG magnitude category: number of bits of |v| (0 for v == 0)
+__device__ __forceinline__ int mag_bits(int v) { return 32 - __clz(abs(v)); }
+
+// number of 0xFF bytes in a 32-bit word (exact zero-byte test on the complement)
+__device__ __forceinline__ unsigned count_ff_bytes(unsigned v)
+{
+    const unsigned x = ~v;
+    const unsigned y = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in every byte of x that is zero
+    return __popc(y);
+}
+
+}  // namespace h2j

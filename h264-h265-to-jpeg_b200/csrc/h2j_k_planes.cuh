@@ -1,0 +1,99 @@
+// K1 (luma variance for the rate control) and the standalone plane conversion kernel.
+#pragma once
+#include "h2j_common.cuh"
+
+namespace h2j {
+
+// ------------------------------------------------------------------------------------------------
+// K1: mb_var_thread (mpegvideo_enc.c) — sum over macroblocks of ((norm1 - sum^2/256 + 628) >> 8)
+// grid (mcu_h, n_frames), one thread per macroblock column, 16 independent 128-bit loads in flight.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mbvar_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
+                                                    FrameState *__restrict__ state)
+{
+    const int f = blockIdx.y, my = blockIdx.x;
+    const uint8_t *Y = frames + (long long)f * L.frame_stride;
+    int local = 0;
+    for (int mx = threadIdx.x; mx < L.mcu_w; mx += blockDim.x) {
+        unsigned sum = 0, norm = 0;
+        const int x0 = mx * 16;
+        if (L.aligned16 && x0 + 16 <= L.w && L.range_mode == 0) {
+            uint4 v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                const int y = min(my * 16 + r, L.h - 1);
+                v[r] = ldg128(Y + (long long)y * L.y_pitch + x0);
+            }
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                sum = __dp4a(v[r].x, 0x01010101u, sum); norm = __dp4a(v[r].x, v[r].x, norm);
+                sum = __dp4a(v[r].y, 0x01010101u, sum); norm = __dp4a(v[r].y, v[r].y, norm);
+                sum = __dp4a(v[r].z, 0x01010101u, sum); norm = __dp4a(v[r].z, v[r].z, norm);
+                sum = __dp4a(v[r].w, 0x01010101u, sum); norm = __dp4a(v[r].w, v[r].w, norm);
+            }
+        } else {
+            for (int r = 0; r < 16; r++) {
+                const int y = min(my * 16 + r, L.h - 1);
+                const uint8_t *row = Y + (long long)y * L.y_pitch;
+                for (int c = 0; c < 16; c++) {
+                    unsigned p = row[min(x0 + c, L.w - 1)];
+                    if (L.range_mode) p = c_range_lut[0][p];
+                    sum += p;
+                    norm += p * p;
+                }
+            }
+        }
+        local += (int)(norm - ((sum * sum) >> 8) + 500u + 128u) >> 8;
+    }
+    // block reduce
+    __shared__ int warp_sums[4];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += warp_sums[i];
+        atomicAdd(&state[f].var_sum, (unsigned long long)t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1 on its own: range conversion + MCU edge replication into padded planes (h2j_convert_pad).
+// One thread per 16 output bytes; 128-bit loads when the source row is 16-byte aligned.
+// grid (ceil(padded_w/16 / 128), padded_h, 3)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) convert_pad_kernel(const uint8_t *__restrict__ frame, FrameLayout L, int range_mode,
+                                                          uint8_t *__restrict__ oy, uint8_t *__restrict__ ou, uint8_t *__restrict__ ov)
+{
+    __shared__ uint8_t s_lut[256];
+    const int plane = blockIdx.z;
+    const int pw = plane ? L.cw : L.w, ph = plane ? L.ch : L.h;
+    const int padw = plane ? L.mcu_w * 8 : L.mcu_w * 16, padh = plane ? L.mcu_h * 8 : L.mcu_h * 16;
+    const int pitch = plane ? L.c_pitch : L.y_pitch;
+    const uint8_t *P = frame + (plane == 0 ? 0 : (plane == 1 ? L.u_off : L.v_off));
+    uint8_t *O = plane == 0 ? oy : (plane == 1 ? ou : ov);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = range_mode ? c_range_lut[plane ? 1 : 0][i] : (uint8_t)i;
+    __syncthreads();
+    const int y = blockIdx.y;
+    if (y >= padh) return;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x0 >= padw) return;
+    const uint8_t *row = P + (long long)min(y, ph - 1) * pitch;
+    uint8_t px[16];
+    if (L.aligned16 && x0 + 16 <= pw) {
+        const uint4 v = ldg128(row + x0);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = row[min(x0 + k, pw - 1)];
+    }
+    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k >> 2] |= (unsigned)s_lut[px[k]] << (8 * (k & 3));
+    *reinterpret_cast<uint4 *>(O + (long long)y * padw + x0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+}  // namespace h2j

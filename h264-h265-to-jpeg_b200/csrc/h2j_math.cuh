@@ -22,19 +22,22 @@ H2J_HD int mulh16(int a, int c) { return (a * c) >> 16; }
 
 // Column pass of ff_fdct_sse2 on one column (x[0..7] = rows), in place.
 // Constants: tg_1_16 = 13036, tg_2_16 = 27146, tg_3_16 = -21746 (tg3 - 1), ocos_4_16 = 23170.
+// The SSE2 code shifts the eight butterfly outputs left (psllw 3, or 4 for t5/t6) before anything else.  Here the
+// shifts are folded into the constants of the multiplies that follow -- ((a << s) * c) >> 16 == (a * (c << s)) >> 16
+// exactly, nothing overflows 32 bits for 8-bit samples -- and into the adds (a * 8 + b is one IMAD/LEA).
 H2J_HD void fdct_col(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &x6, int &x7)
 {
-    const int t0 = (x0 + x7) << 3, t1 = (x1 + x6) << 3, t2 = (x2 + x5) << 3, t3 = (x3 + x4) << 3;
-    const int t7 = (x0 - x7) << 3, t6 = (x1 - x6) << 4, t5 = (x2 - x5) << 4, t4 = (x3 - x4) << 3;
-    const int tm12 = t1 - t2, tp12 = t1 + t2, tm03 = t0 - t3, tp03 = t0 + t3;
-    const int y0 = tp03 + tp12;
-    const int y4 = tp03 - tp12;
-    const int y2 = (mulh16(tm12, 27146) + tm03) | 1;
-    const int y6 = (mulh16(tm03, 27146) - tm12) | 1;
-    const int tp65 = mulh16(t6 + t5, 23170) | 1;
-    const int tm65 = mulh16(t6 - t5, 23170);
-    const int tp465 = t4 + tm65, tm465 = t4 - tm65;
-    const int tm765 = t7 - tp65, tp765 = t7 + tp65;
+    const int s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
+    const int d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
+    const int um12 = s1 - s2, up12 = s1 + s2, um03 = s0 - s3, up03 = s0 + s3;   // tm12 = um12 << 3, ...
+    const int y0 = (up03 + up12) * 8;
+    const int y4 = (up03 - up12) * 8;
+    const int y2 = (((um12 * (27146 * 8)) >> 16) + um03 * 8) | 1;
+    const int y6 = (((um03 * (27146 * 8)) >> 16) - um12 * 8) | 1;
+    const int tp65 = (((d1 + d2) * (23170 * 16)) >> 16) | 1;                     // t5, t6 carry << 4
+    const int tm65 = ((d1 - d2) * (23170 * 16)) >> 16;
+    const int tp465 = d3 * 8 + tm65, tm465 = d3 * 8 - tm65;
+    const int tm765 = d0 * 8 - tp65, tp765 = d0 * 8 + tp65;
     const int y1 = (mulh16(tp465, 13036) + tp765) | 1;
     const int y3 = tm765 - (mulh16(tm465, -21746) + tm465);
     const int y5 = (mulh16(tm765, -21746) + tm765) + tm465;
@@ -95,14 +98,13 @@ H2J_HD void fdct_8x8(int (&v)[64])
 // bq in the high 16 bits.
 H2J_HD uint32_t quant_pack(uint32_t qmat16, uint32_t bias16) { return qmat16 | ((bias16 * qmat16) << 16); }
 
-H2J_HD int quant_ac(int x, uint32_t packed)
+H2J_HD int quant_ac2(int x, int q, int bq)
 {
-    const int q = (int)(packed & 0xffffu);
-    const int bq = (int)(packed >> 16);
     const int s = x >> 31;                 // 0 or -1
     const int c = bq ^ (s & 0xffff);       // bq or 65535 - bq
     return (x * q + c) >> 16;
 }
+H2J_HD int quant_ac(int x, uint32_t packed) { return quant_ac2(x, (int)(packed & 0xffffu), (int)(packed >> 16)); }
 // DC: ((block[0] >> 2) + q) * ff_inverse[2q] >> 32 with q = 8  ==  ((x >> 2) + 8) >> 4  (x >= 0)
 H2J_HD int quant_dc(int x) { return ((x >> 2) + 8) >> 4; }
 

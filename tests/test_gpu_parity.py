@@ -85,3 +85,26 @@ def test_batch_of_different_frames(enc, orc):
     for (y, u, v), got in zip(planes, res.jpegs):
         want, _, _ = orc.oracle_encode(y, u, v)
         assert got == want
+
+
+def test_dense_tiles_take_the_windowed_path(orc):
+    """Noise at qscale 1 needs far more than 64 Kibit per 192-block tile, so K4 runs its windowed emission."""
+    import h2j_b200
+
+    w, h = 272, 208
+    y, u, v = orc.synth_planes(w, h, "noise", seed=31, amp=127)
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=2, n_slots=1, fixed_qscale=1, max_jpeg_bytes=8 * 1024 * 1024) as e:
+        got = _compare(e, orc, y, u, v, fixed_qscale=1)
+        info = e.frame_info(0, 0)
+    n_tiles = -(-info.mcu_w * info.mcu_h * 6 // 192)
+    assert info.scan_bits / n_tiles > 65536, "the case no longer exercises the windowed path"
+    assert len(got) > 0
+
+
+def test_fixed_qscale_range(orc):
+    import h2j_b200
+
+    y, u, v = orc.synth_planes(160, 96, "textured", seed=5, amp=60)
+    for q in (1, 3, 31):
+        with h2j_b200.Encoder(max_width=160, max_height=96, max_batch=1, n_slots=1, fixed_qscale=q) as e:
+            _compare(e, orc, y, u, v, fixed_qscale=q)
