@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sub-batch", type=int, default=64, help="frames per submitted batch")
     ap.add_argument("--slots", type=int, default=4, help="batches in flight (streams)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall time the CPU baseline sample should take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -183,10 +184,13 @@ def run_reference_arm(a):
     w, h = a.width, a.height
     cores = os.cpu_count() or 1
     frames = make_frames_numpy(8, w, h)
-    # bounded sample per step: about 2 frames per core so that warmup+steps finish within minutes
-    n = a.cpu_frames or max(2 * cores, 16)
+    # bounded sample per step: sized from a calibration pass so that warmup + steps take about a minute in all
+    n0 = max(2 * cores, 16)
+    dt0, _, _ = cpu_encode_sample(frames, w, h, n0, cores)
+    per_step_s = min(6.0, 60.0 / max(1, a.steps + a.warmup))
+    n = a.cpu_frames or max(n0, int(per_step_s * n0 / dt0))
     for _ in range(a.warmup):
-        cpu_encode_sample(frames, w, h, max(cores, 8), cores)
+        cpu_encode_sample(frames, w, h, n, cores)
     times = []
     kind = "port"
     for _ in range(a.steps):
@@ -230,7 +234,9 @@ def run_ours(a):
     F, SB, NS = a.frames, a.sub_batch, a.slots
     assert F % SB == 0
     nsub = F // SB
-    d_frames, fb, stride = make_frames_torch(F, w, h, dev, seed0=rank * F)
+    lo, hi = h2j_b200.shard_range(world * F, rank, world)  # the job is world*F distinct frames, sharded per image
+    assert hi - lo == F
+    d_frames, fb, stride = make_frames_torch(F, w, h, dev, seed0=lo)
     torch.cuda.synchronize()
 
     enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=SB, n_slots=NS, device=local_rank, profile=True)
@@ -402,11 +408,13 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = a.cpu_frames or max(4 * cores, 32)
         host8 = d_frames[:8, :fb].cpu().numpy()
-        cpu_encode_sample(host8, w, h, min(n, 2 * cores), cores)  # warm
+        n0 = max(4 * cores, 32)
+        dt0, _, _ = cpu_encode_sample(host8, w, h, n0, cores)  # warm + calibrate
+        n = a.cpu_frames or max(n0, int(a.cpu_seconds * n0 / dt0))
         dt, kind, _ = cpu_encode_sample(host8, w, h, n, cores)
-        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{n} of the bench frames, {cores} host threads, {dt:.1f} s"}
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n} frames (8 of the bench frames, cycled) on {cores} host threads, {dt:.1f} s of wall time"}
 
     if rank == 0:
         line = {

@@ -136,6 +136,24 @@ def split_planes(frame: np.ndarray, width: int, height: int) -> Tuple[np.ndarray
     return y, u, v
 
 
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Per-image sharding of a job over the ranks of one box: the half-open range of item indices rank `rank` owns.
+    Images are independent, so this is the whole multi-GPU plan -- no collective touches the data path.  The first
+    ``n_items % world`` ranks take one extra item; ranges are contiguous, disjoint and cover [0, n_items)."""
+    if world < 1 or not (0 <= rank < world) or n_items < 0:
+        raise ValueError(f"bad shard request: n_items={n_items} rank={rank} world={world}")
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sub_batches(lo: int, hi: int, max_batch: int) -> List[Tuple[int, int]]:
+    """Cut a rank's range into submit-sized pieces (each at most `max_batch` frames), in order."""
+    if max_batch < 1:
+        raise ValueError("max_batch must be >= 1")
+    return [(s, min(s + max_batch, hi)) for s in range(lo, hi, max_batch)]
+
+
 class PinnedBuffer:
     """Page-locked host memory exposed as a numpy uint8 array."""
 

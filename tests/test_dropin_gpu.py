@@ -1,0 +1,58 @@
+"""GPU suite: the boundary.  (1) host/Encoder.cpp -- the C++ mirror of the reference's Encoder class -- through its
+C shim; (2) the DROP-IN: the reference's own src/Decoder.cpp + JNI bridge compiled against this repo's Encoder
+(host/Makefile target `dropin`), driven through the unchanged IDecoder::H265ToJpeg(in, out) on the reference's own
+test/img fixtures (copied next to the .so at build time), compared byte for byte with what the unmodified
+reference (oracle/_ref/libh2j_ref.so) writes for the same file."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "h264-h265-to-jpeg_b200", "lib", "libh2j_host.so")
+DROPIN_DIR = os.path.join(ROOT, "oracle", "_ref", "dropin")
+DROPIN_SO = os.path.join(DROPIN_DIR, "libH265ToJpeg_b200.so")
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_host_encoder_class_writes_the_oracle_bytes(orc, tmp_path):
+    assert os.path.exists(HOST_SO), "libh2j_host.so missing: run __graft_entry__.build()"
+    lib = C.CDLL(HOST_SO)
+    lib.h2j_host_yuv2jpeg_file.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    for (w, h, fmt) in ((322, 242, 0), (1920, 1080, 12), (2562, 1442, 0)):  # the last one makes the shared encoder grow
+        y, u, v = orc.synth_planes(w, h, "textured", seed=w, amp=35)
+        out = str(tmp_path / f"o_{w}.jpeg")
+        assert lib.h2j_host_yuv2jpeg_file(y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], w, h, fmt,
+                                          out.encode()) == 1
+        want, _, _ = orc.oracle_encode(y, u, v)
+        assert open(out, "rb").read() == want
+    # error behaviour of the reference class: false, no file, on a bad path / bad format
+    y, u, v = orc.synth_planes(64, 64, "textured", seed=1)
+    assert lib.h2j_host_yuv2jpeg_file(y.ctypes.data, 64, u.ctypes.data, 32, v.ctypes.data, 32, 64, 64, 0, b"") == 0
+    assert lib.h2j_host_yuv2jpeg_file(y.ctypes.data, 64, u.ctypes.data, 32, v.ctypes.data, 32, 64, 64, 2, str(tmp_path / "x.jpeg").encode()) == 0
+    assert not os.path.exists(tmp_path / "x.jpeg")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_SO), reason="drop-in library not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name", ["img01.h264", "img01.h265"])
+def test_dropin_library_on_the_reference_fixtures(orc, name, tmp_path):
+    lib = C.CDLL(DROPIN_SO)
+    lib.dropin_h265_to_jpeg.argtypes = [C.c_char_p, C.c_char_p]
+    src = os.path.join(DROPIN_DIR, "fixtures", name)
+    out = str(tmp_path / (name + ".jpeg"))
+    assert lib.dropin_h265_to_jpeg(src.encode(), out.encode()) == 1
+    got = open(out, "rb").read()
+    # (a) against the committed golden digest of the reference's full-frame JPEG
+    z = np.load(os.path.join(G, "ref_img_crops.npz"))
+    key = name.replace(".", "_")
+    assert hashlib.sha256(got).hexdigest() == z[key + "_full_sha256"].tobytes().decode()
+    assert len(got) == int(z[key + "_full_dims"][2])
+    # (b) against the unmodified reference run live on the same file, when it travelled to this box
+    if orc.have_reference():
+        ref_out = str(tmp_path / (name + ".ref.jpeg"))
+        assert orc.reference().ref_h265_to_jpeg(src.encode(), ref_out.encode(), 1) == 1
+        assert got == open(ref_out, "rb").read()

@@ -14,7 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def shim(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("shim") / "libmathshim.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(HERE, "support", "math_shim.cpp")], check=True)
-    return C.CDLL(so)
+    lib = C.CDLL(so)
+    lib.shim_fdct.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.shim_quant.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.shim_matrix.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
 
 
 def _blocks():
