@@ -46,8 +46,11 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
-    ap.add_argument("--sub-batch", type=int, default=64, help="frames per submitted batch")
-    ap.add_argument("--slots", type=int, default=4, help="batches in flight (streams)")
+    ap.add_argument("--sub-batch", type=int, default=0, help="frames per submitted batch of the device-resident pass (0 = --frames)")
+    ap.add_argument("--slots", type=int, default=1, help="batches in flight (streams) of the device-resident pass; 1 keeps the per-kernel "
+                                                         "CUDA-event brackets free of other streams' kernels")
+    ap.add_argument("--e2e-sub-batch", type=int, default=64, help="frames per submitted batch of the host-to-host pass")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight of the host-to-host pass (overlaps H2D, kernels, D2H)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall time the CPU baseline sample should take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,8 +234,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
 
     w, h = a.width, a.height
-    F, SB, NS = a.frames, a.sub_batch, a.slots
-    assert F % SB == 0
+    F, SB, NS = a.frames, a.sub_batch or a.frames, a.slots
+    assert F % SB == 0 and F % a.e2e_sub_batch == 0
     nsub = F // SB
     lo, hi = h2j_b200.shard_range(world * F, rank, world)  # the job is world*F distinct frames, sharded per image
     assert hi - lo == F
@@ -327,24 +330,29 @@ def run_ours(a):
     # ---- e2e: pinned host in, pinned host out ------------------------------------------------------
     e2e = None
     if not a.no_e2e:
+        ESB, ENS = a.e2e_sub_batch, a.e2e_slots
+        ensub = F // ESB
+        enc.close()
+        enc2 = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=ESB, n_slots=ENS, device=local_rank)
         h_in = h2j_b200.PinnedBuffer(F * stride)
         h_in.array[:] = d_frames.reshape(-1).cpu().numpy()
-        out_cap = SB * 2 * 1024 * 1024
-        h_out = [h2j_b200.PinnedBuffer(out_cap) for _ in range(NS)]
+        out_cap = ESB * 2 * 1024 * 1024
+        h_out = [h2j_b200.PinnedBuffer(out_cap) for _ in range(ENS)]
         d2h = [0]
+        launches_e2e0 = enc2.kernel_launches
 
         def e2e_step():
             inflight = []
-            for i in range(nsub):
-                slot = i % NS
-                if len(inflight) == NS:
+            for i in range(ensub):
+                slot = i % ENS
+                if len(inflight) == ENS:
                     s0 = inflight.pop(0)
-                    offs, st = enc.collect_into(s0, h_out[s0].ptr, out_cap)
+                    offs, st = enc2.collect_into(s0, h_out[s0].ptr, out_cap)
                     d2h[0] += int(offs[-1])
-                enc.submit_host(slot, h_in.ptr + i * SB * stride, stride, SB, w, h)
+                enc2.submit_host(slot, h_in.ptr + i * ESB * stride, stride, ESB, w, h)
                 inflight.append(slot)
             for s0 in inflight:
-                offs, st = enc.collect_into(s0, h_out[s0].ptr, out_cap)
+                offs, st = enc2.collect_into(s0, h_out[s0].ptr, out_cap)
                 d2h[0] += int(offs[-1])
 
         for _ in range(a.warmup):
@@ -362,7 +370,11 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_max = float(t.item())
         e2e = {"value": world * F * a.steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": world * F * fb,
-               "d2h_bytes_per_step": world * d2h[0] // a.steps, "timing": "wall clock between device synchronisations, max over ranks"}
+               "d2h_bytes_per_step": world * d2h[0] // a.steps, "timing": "wall clock between device synchronisations, max over ranks",
+               "sub_batch": ESB, "slots": ENS, "h2d_gbs": world * F * fb * a.steps / dt_max / 1e9,
+               "note": "host-pinned I420 in, packed JPEG bytes out to pinned host memory, every step; bound by the H2D copy "
+                       "(3.11 MB of pixels per frame over PCIe)"}
+        enc2.close()
         h_in.free()
         for b in h_out:
             b.free()
@@ -380,8 +392,8 @@ def run_ours(a):
     avg_jpeg = sizes_total[0] / max(1, F * a.steps)
     alg_bytes = {  # per frame; DESIGN.md section 5
         "mbvar_kernel": w * h,
-        "fdct_quant_kernel": fb + nblk * (132 + 8),
-        "entropy_kernel": nblk * (132 + 8) + avg_jpeg,
+        "fdct_quant_kernel": fb + nblk * 136,
+        "entropy_kernel": nblk * 136 + avg_jpeg,
         "stuff_kernel": 2 * avg_jpeg,
         "huffman_kernel": nblk * 2,
     }
@@ -398,8 +410,9 @@ def run_ours(a):
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": per_kernel[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes[dom] * SB,
-            "note": "per-kernel CUDA events on the launching stream inside the timed region; with several slots in flight a bracket "
-                    "can include a neighbour stream's kernels, so this is a lower bound on the kernel's own rate"}
+            "note": "per-kernel CUDA events on the launching stream inside the timed region (one slot: no other stream's kernels "
+                    "inside a bracket)" if NS == 1 else "per-kernel CUDA events on the launching stream; several slots in flight, so a "
+                    "bracket can include a neighbour stream's kernels (lower bound on the kernel's own rate)"}
     for k in ("fdct_quant_kernel", "mbvar_kernel", "entropy_kernel"):
         if k in per_kernel and "gbs" in per_kernel[k]:
             roof[k + "_frac"] = per_kernel[k]["gbs"] / peak
@@ -431,7 +444,7 @@ def run_ours(a):
             "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
-    enc.close()
+    enc.close()  # (idempotent: already closed when the host-to-host pass ran)
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,7 +30,6 @@ struct Slot {
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
     uint8_t *d_frames = nullptr;  // staging for host submits
     uint32_t *d_images = nullptr;  // [max_batch][images_cap] tile images (h2j_common.cuh)
-    unsigned long long *d_masks = nullptr;
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
@@ -71,6 +70,7 @@ struct h2j_encoder {
     int tiles_cap = 0;            // K4 tiles per frame at max geometry
     int chunks_cap = 0;           // K5 chunks per frame
     int stuff_ctas = 32;          // K5 CTAs per frame
+    int fdct_tiles_per_cta = 8;   // consecutive K2 tiles one CTA walks (amortises its set-up and histogram flush)
     size_t frame_bytes_cap = 0;
     uint8_t *d_qscale_lut = nullptr;
     char *d_comment = nullptr;
@@ -213,9 +213,9 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
     {
         ScopedTiming t(e, sl, "fdct_quant_kernel");
-        const int tiles_per_cta = 4;
+        const int tiles_per_cta = e->fdct_tiles_per_cta;
         fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, 0, st>>>(
-            d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs, sl.d_images, sl.d_masks, e->images_cap, e->blocks_cap, tiles_per_cta);
+            d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }
     {
@@ -227,9 +227,9 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
         ScopedTiming t(e, sl, "entropy_kernel");
-        entropy_kernel<<<tiles_per_frame * n, kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_state, sl.d_images, e->images_cap, sl.d_masks,
-                                                                               e->blocks_cap, sl.d_descs, sl.d_ticket, tiles_per_frame, sl.d_scan,
-                                                                               e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
+        entropy_kernel<<<tiles_per_frame * n, kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_state, sl.d_images, e->images_cap, sl.d_descs,
+                                                                               sl.d_ticket, tiles_per_frame, sl.d_scan, e->scan_cap_words,
+                                                                               sl.d_chunk_ff, e->chunks_cap);
         e->launches++;
     }
     {
@@ -275,7 +275,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_masks); cudaFree(sl.d_zero);
+    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_zero);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -409,9 +409,8 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
         CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
-        CUB(cudaMalloc(&sl.d_masks, (size_t)e->blocks_cap * B * sizeof(unsigned long long)));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
-        const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->tiles_cap * B, 256);
+        const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->tiles_cap * 2 * B, 256);  // length + tail word per tile
         const size_t chunk_bytes = align_up(sizeof(unsigned int) * (size_t)e->chunks_cap * B, 256);
         sl.zero_bytes = state_bytes + desc_bytes + 256 + chunk_bytes;
         CUB(cudaMalloc(&sl.d_zero, sl.zero_bytes));
@@ -619,10 +618,10 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
     if (rc) return rc;
     CU(e, cudaMemcpyAsync(sl.d_frames, sl.h_stage, fb, cudaMemcpyHostToDevice, sl.stream));
     const int pw = L.mcu_w * 16, ph = L.mcu_h * 16;
-    // padded planes are produced in the (otherwise idle) JPEG output buffer
+    // padded planes are produced in the (otherwise idle) coefficient buffer: 136 bytes per 64 samples, always enough
     const size_t need = (size_t)pw * ph * 3 / 2;
-    if (need > e->out_cap * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's output buffer");
-    uint8_t *oy = sl.d_out, *ou = oy + (size_t)pw * ph, *ov = ou + (size_t)pw * ph / 4;
+    if (need > (size_t)e->images_cap * kTileImageBytes * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's scratch buffer");
+    uint8_t *oy = reinterpret_cast<uint8_t *>(sl.d_images), *ou = oy + (size_t)pw * ph, *ov = ou + (size_t)pw * ph / 4;
     convert_pad_kernel<<<dim3((pw / 16 + 127) / 128, ph, 3), 128, 0, sl.stream>>>(sl.d_frames, L, range_mode, oy, ou, ov);
     e->launches++;
     CU(e, cudaGetLastError());

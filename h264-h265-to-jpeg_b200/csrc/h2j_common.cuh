@@ -34,19 +34,23 @@ struct FrameLayout {
 
 // ---- coefficient store ("tile images") -----------------------------------------------------------
 // K2 works on tiles of 16 consecutive MCUs (96 blocks, coding order).  A tile leaves K2 as one contiguous
-// image of 96 block records, 33 words each:
-//   word j (0..31)  low half: level j, high half: level j + 32 of the zigzag scan (this pairing lets K2 derive
-//                   the non-zero mask from packed 16-bit minima); level 0 is stored as the DC *difference* to the
-//                   previous block of the same component, i.e. what gets coded
-//   word 32         padding: makes the record stride odd in words, so that K4's per-thread reads of
-//                   "coefficient k of my block" from the image in shared memory are bank-conflict free
-// K4 pulls two images (192 blocks) into shared memory with one bulk copy.
+// image: 96 block records of 33 words each, then 96 words of high mask halves.
+//   record word j (0..31)  low half: level j, high half: level j + 32 of the zigzag scan (this pairing lets K2
+//                          derive the non-zero mask from packed 16-bit minima); level 0 is stored as the DC
+//                          *difference* to the previous block of the same component, i.e. what gets coded
+//   record word 32         non-zero mask of levels 1..31 (bit k = level k != 0, bit 0 clear).  It also makes the
+//                          record stride odd in words, so K4's per-thread reads of "coefficient k of my block"
+//                          from the image in shared memory are bank-conflict free
+//   word 3168 + b          non-zero mask of levels 32..63 of block b
+// The image is assembled in shared memory and moved with ONE bulk (TMA) store by K2 and ONE bulk load by K4.
 constexpr int kTileMcus = 16;
 constexpr int kTileBlocks = kTileMcus * 6;                  // 96
 constexpr int kBlkWords = 33;
 constexpr int kBlkHalf = kBlkWords * 2;                     // 66
-constexpr int kTileImageWords = kTileBlocks * kBlkWords;    // 3168
-constexpr int kTileImageBytes = kTileImageWords * 4;        // 12672 = 792 * 16
+constexpr int kMaskLoWord = 32;                             // inside the record
+constexpr int kMaskHiOff = kTileBlocks * kBlkWords;         // 3168
+constexpr int kTileImageWords = kMaskHiOff + kTileBlocks;   // 3264
+constexpr int kTileImageBytes = kTileImageWords * 4;        // 13056 = 816 * 16
 constexpr int kFdctThreads = kTileBlocks;
 
 constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
@@ -121,5 +125,50 @@ __device__ __forceinline__ unsigned count_ff_bytes(unsigned v)
     const unsigned y = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in every byte of x that is zero
     return __popc(y);
 }
+
+// ---- mbarrier + bulk copy (TMA engine, 1-D) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// shared -> global bulk store (TMA engine), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's bulk stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed altogether
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) -- every writer, before the barrier
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace h2j

@@ -1,48 +1,35 @@
 // K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame).
 //
-// A tile is 192 consecutive blocks of one frame (two K2 tile images).  One elected thread pulls the images into
-// shared memory with a single bulk copy (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier while the other
-// threads fetch the frame's code tables and their block's non-zero mask.
-//   1. every thread walks the non-zero mask of its block and sums code lengths; block-wide exclusive scan.
-//   2. threads emit their codes into the tile's shared-memory bit buffer.
-//   3. the tile publishes (length, trailing bits) and resolves its exclusive prefix by decoupled look-back over
-//      the frame's earlier tiles (tiles are handed out through an atomic ticket, so every predecessor is running).
-//   4. the buffer is shifted to the tile's global bit position and stored as big-endian words; a 32-bit word is
-//      written by the tile that holds its last bit, with the bits of earlier tiles arriving through the look-back
-//      payload -- no atomics on the scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are
+// A tile is 192 consecutive blocks of one frame (two K2 tile images).  One elected thread pulls the images (levels
+// and non-zero masks) into shared memory with a single bulk copy (cp.async.bulk -> SASS UBLKCP) signalled on an
+// mbarrier while the other threads fetch the frame's code tables and clear the bit window.
+//   1. every thread walks the non-zero mask of its block and sums code lengths; block-wide exclusive scan.  The
+//      tile's bit length is published at once, and warp 0 issues its look-back loads (tiles are handed out through
+//      an atomic ticket, so every predecessor is already running).
+//   2. threads emit their codes into the tile's shared-memory bit window.
+//   3. warp 0 publishes the tile's trailing 31 bits, resolves the exclusive prefix from the loads issued in 1
+//      (decoupled look-back; by now the predecessors have long published their lengths) and fetches the trailing
+//      bits of the tile in front -- the only thing that depends on a neighbour's emission.
+//   4. the window is shifted to the tile's global bit position and stored as big-endian words; a 32-bit word is
+//      written by the tile that holds its last bit, with the bits of the tile in front taken from its published
+//      tail -- no atomics on the scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are
 //      counted into per-chunk counters for K5.
-// The bit buffer holds 64 Kibit.  A tile that needs more (> 341 bits per block on average; the reference's own
+// The bit window holds 64 Kibit.  A tile that needs more (> 341 bits per block on average; the reference's own
 // 2 MiB output cap is hit first at 1080p) takes the windowed path: the same emission clipped to one window of the
 // tile's bit range at a time.
 //
-// Descriptor (one 64-bit word, so a single relaxed store/load carries everything):
-//   [63:62] status (0 invalid, 1 tile aggregate, 2 inclusive prefix)   [61:31] bit length   [30:0] last 31 bits
+// Descriptors (64-bit words, so a single relaxed store/load carries everything), two per tile:
+//   length word  [63:62] status (0 invalid, 1 tile length, 2 inclusive prefix length)   [31:0] bits
+//   tail word    [63] valid   [30:0] the tile's last 31 bits (every tile but a frame's last is longer than that:
+//                192 blocks of at least two bits each)
 #pragma once
 #include "h2j_common.cuh"
 
 namespace h2j {
 
-struct BitRun { unsigned int len; unsigned int tail; };  // tail: the last min(len,31) bits, right aligned
-
-__device__ __forceinline__ BitRun bitrun_concat(BitRun x, BitRun y)  // x then y
-{
-    BitRun r;
-    r.len = x.len + y.len;
-    r.tail = (y.len >= 31) ? y.tail : (((x.tail << y.len) | y.tail) & 0x7fffffffu);
-    return r;
-}
-__device__ __forceinline__ unsigned long long desc_pack(unsigned status, BitRun r)
-{
-    return ((unsigned long long)status << 62) | ((unsigned long long)r.len << 31) | (unsigned long long)(r.tail & 0x7fffffffu);
-}
+__device__ __forceinline__ unsigned long long desc_pack(unsigned status, unsigned len) { return ((unsigned long long)status << 62) | len; }
 __device__ __forceinline__ unsigned desc_status(unsigned long long d) { return (unsigned)(d >> 62); }
-__device__ __forceinline__ BitRun desc_run(unsigned long long d)
-{
-    BitRun r;
-    r.len = (unsigned)((d >> 31) & 0x7fffffffu);
-    r.tail = (unsigned)(d & 0x7fffffffu);
-    return r;
-}
+__device__ __forceinline__ unsigned desc_len(unsigned long long d) { return (unsigned)d; }
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p)
 {
     unsigned long long v;
@@ -52,38 +39,6 @@ __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *
 __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// ---- mbarrier + bulk copy (TMA engine, 1-D) -------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
 }
 
 // ---- bit sinks ------------------------------------------------------------------------------------
@@ -227,23 +182,23 @@ __device__ __forceinline__ bool store_run(const unsigned int *s_bits, unsigned P
 }
 
 constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + (kEntWinWords + 4) * 4;
+constexpr int kEntPreZeroWords = 768;  // cleared while the bulk load is in flight; covers 128 bits per block
 
 __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
                                                               const uint32_t *__restrict__ images, long long images_cap,
-                                                              const unsigned long long *__restrict__ masks, long long blocks_cap,
-                                                              unsigned long long *__restrict__ descs,  // [frame][tiles_per_frame]
+                                                              unsigned long long *__restrict__ descs,  // [frame][2][tiles_per_frame]
                                                               unsigned int *__restrict__ ticket, int tiles_per_frame,
                                                               uint32_t *__restrict__ scan, long long scan_cap_words,
                                                               unsigned int *__restrict__ chunk_ff, int chunks_cap)
 {
-    extern __shared__ __align__(16) unsigned char ent_smem[];
+    extern __shared__ __align__(128) unsigned char ent_smem[];
     uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                   // two tile images
     unsigned int *s_bits = reinterpret_cast<unsigned int *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [0] guard, [1..] bits
     __shared__ uint32_t s_hdc[2][16];
     __shared__ uint32_t s_hac[2][256];
     __shared__ unsigned s_warp[kEntThreads / 32];
     __shared__ unsigned s_ticket;
-    __shared__ BitRun s_excl;
+    __shared__ unsigned s_excl_len;
     __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -263,19 +218,21 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
     const FrameTab *T = tabs + f;
     for (int i = tid; i < 512; i += kEntThreads) (&s_hac[0][0])[i] = T->hcode[2 + (i >> 8)][i & 255];
     if (tid < 32) (&s_hdc[0][0])[tid] = T->hcode[tid >> 4][tid & 15];
+    for (int i = tid; i < kEntPreZeroWords; i += kEntThreads) s_bits[i] = 0;
 
     const int b = tile * kEntBlocks + tid;
     const bool valid = b < L.n_blocks;
-    unsigned mask_lo = 0, mask_hi = 0;
-    if (valid) {
-        const unsigned long long m = masks[(long long)f * blocks_cap + b];
-        mask_lo = (unsigned)m;
-        mask_hi = (unsigned)(m >> 32);
-    }
+    const int img_i = tid >= kTileBlocks ? 1 : 0, rec_i = tid - img_i * kTileBlocks;
+    const uint32_t *rec = s_img + img_i * kTileImageWords + rec_i * kBlkWords;
     const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
-    const int16_t *cb = reinterpret_cast<const int16_t *>(s_img) + tid * kBlkHalf;
+    const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
     __syncthreads();      // tables in shared memory
     mbar_wait(&s_bar, 0); // coefficient images landed
+    unsigned mask_lo = 0, mask_hi = 0;
+    if (valid) {
+        mask_lo = rec[kMaskLoWord];
+        mask_hi = s_img[img_i * kTileImageWords + kMaskHiOff + rec_i];
+    }
 
     // ---- 1. lengths ----
     unsigned len = 0;
@@ -297,12 +254,24 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
     const unsigned off = warp_off + incl - len;
     const bool windowed = tile_len > (unsigned)kEntWinBits;
 
-    // ---- 2. bits of the tile (or, windowed, only its last 64 bits: enough for the descriptor) ----
+    // the length is all a successor's look-back needs: publish it now, and start our own look-back loads
+    unsigned long long *D = descs + (long long)f * tiles_per_frame * 2;  // length words
+    unsigned long long *TW = D + tiles_per_frame;                        // tail words
+    unsigned long long d_look = 0;
+    if (warp == 0) {
+        if (lane == 0) st_desc(&D[tile], desc_pack(tile > 0 ? 1 : 2, tile_len));
+        const int idx = tile - 1 - lane;
+        d_look = idx >= 0 ? ld_desc(&D[idx]) : desc_pack(2, 0);
+    }
+
+    // ---- 2. bits of the tile (or, windowed, only its last 64 bits: enough for the tail word) ----
     unsigned own_tail;
     if (!windowed) {
         const int n_words = (int)((tile_len + 31) >> 5);
-        for (int i = tid; i <= n_words + 1; i += kEntThreads) s_bits[i] = 0;
-        __syncthreads();
+        if (n_words + 2 > kEntPreZeroWords) {  // uniform across the CTA
+            for (int i = kEntPreZeroWords + tid; i <= n_words + 1; i += kEntThreads) s_bits[i] = 0;
+            __syncthreads();
+        }
         if (valid) {
             BitSink sink;
             sink.init(s_bits + 1, off);
@@ -312,8 +281,6 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         __syncthreads();
         own_tail = stream_tail(s_bits, tile_len);
     } else {
-        if (tid < 4) s_bits[tid] = 0;
-        __syncthreads();
         const unsigned lo = tile_len - 64;
         if (valid && off + len > lo) {
             BitSinkClip sink;
@@ -324,66 +291,58 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         own_tail = s_bits[2] & 0x7fffffffu;
     }
 
-    // ---- 3. publish aggregate, resolve exclusive prefix (warp 0) ----
-    unsigned long long *D = descs + (long long)f * tiles_per_frame;
+    // ---- 3. publish the tail, resolve the exclusive prefix, fetch the tail of the tile in front (warp 0) ----
     if (warp == 0) {
-        BitRun own;
-        own.len = tile_len;
-        own.tail = own_tail;
-        if (lane == 0 && tile > 0) st_desc(&D[tile], desc_pack(1, own));
-        BitRun excl;
-        excl.len = 0;
-        excl.tail = 0;
+        if (lane == 0) st_desc(&TW[tile], (1ull << 63) | own_tail);
+        unsigned excl = 0;
         if (tile > 0) {
-            BitRun running;
-            running.len = 0;
-            running.tail = 0;
             int basei = tile - 1;
+            unsigned long long d = d_look;
             while (true) {
                 const int idx = basei - lane;
-                unsigned long long d;
                 if (idx >= 0) {
-                    do { d = ld_desc(&D[idx]); } while (desc_status(d) == 0);
-                } else {
-                    BitRun z; z.len = 0; z.tail = 0;
-                    d = desc_pack(2, z);
-                }
+                    while (desc_status(d) == 0) d = ld_desc(&D[idx]);
+                } else d = desc_pack(2, 0);
                 const unsigned pm = __ballot_sync(0xffffffffu, desc_status(d) == 2);
                 const int stop = pm ? (__ffs(pm) - 1) : 31;
-                BitRun acc = running;
-                for (int l = 0; l <= stop; l++) {
-                    const unsigned long long dl = __shfl_sync(0xffffffffu, d, l);
-                    acc = bitrun_concat(desc_run(dl), acc);
-                }
-                running = acc;
+                unsigned part = lane <= stop ? desc_len(d) : 0u;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
                 if (pm) break;
                 basei -= 32;
+                const int idx2 = basei - lane;
+                d = idx2 >= 0 ? ld_desc(&D[idx2]) : desc_pack(2, 0);
             }
-            excl = running;
         }
         if (lane == 0) {
-            st_desc(&D[tile], desc_pack(2, bitrun_concat(excl, own)));
-            s_excl = excl;
-            if (tile == tiles_per_frame - 1) state[f].scan_bits = (unsigned long long)excl.len + tile_len;
+            if (tile > 0) st_desc(&D[tile], desc_pack(2, excl + tile_len));
+            unsigned tail_in = 0;
+            if (tile > 0 && (excl & 31)) {
+                unsigned long long t;
+                do { t = ld_desc(&TW[tile - 1]); } while ((t >> 63) == 0);
+                tail_in = (unsigned)t & 0x7fffffffu;
+            }
+            s_excl_len = excl;
+            s_bits[0] = tail_in;  // bits of the tile in front living in our first word
+            if (tile == tiles_per_frame - 1) state[f].scan_bits = (unsigned long long)excl + tile_len;
         }
     }
     __syncthreads();
 
     // ---- 4. shift to the global bit position, store, count 0xFF bytes ----
-    const unsigned P = s_excl.len;
+    const unsigned P = s_excl_len;
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
     const bool last_tile = tile == tiles_per_frame - 1;
     bool overflow = false;
     if (!windowed) {
-        if (tid == 0) s_bits[0] = s_excl.tail;  // bits of earlier tiles living in the first word
-        __syncthreads();
         overflow = store_run(s_bits, P, tile_len, last_tile, gs, scan_cap_words, cff, tid);
     } else {
-        unsigned tail_in = s_excl.tail;
+        unsigned tail_in = s_bits[0];
         for (unsigned lo = 0; lo < tile_len; lo += kEntWinBits) {
             const unsigned hi = min(lo + (unsigned)kEntWinBits, tile_len);
-            __syncthreads();  // previous window fully stored
+            __syncthreads();  // previous window fully stored (first round: everybody has read s_bits[0])
             for (int i = tid; i <= kEntWinWords + 2; i += kEntThreads) s_bits[i] = 0;
             __syncthreads();
             if (valid && off < hi && off + len > lo) {

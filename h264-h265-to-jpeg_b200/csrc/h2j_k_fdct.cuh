@@ -1,58 +1,27 @@
 // K2: pixels -> quantised zigzag coefficients, DC differences and symbol statistics.
 //
-// One thread owns one 8x8 block with all 64 values in registers.  A tile is 16 consecutive MCUs in coding
-// order (it may wrap to the next MCU row):
-//   warp 0: Y0/Y1 of the 16 MCUs  (32 horizontally adjacent blocks -> 256 contiguous bytes per pixel row)
-//   warp 1: Y2/Y3
+// One thread owns one 8x8 block with all 64 values in registers.  A tile is 16 consecutive MCUs in coding order
+// (it may wrap to the next MCU row); a CTA of three warps walks `tiles_per_cta` consecutive tiles:
+//   warp 0: the four luma blocks of MCUs 0..7   (lane = mcu * 4 + n: lane order IS coding order)
+//   warp 1: the four luma blocks of MCUs 8..15
 //   warp 2: Cb of the 16 MCUs (lanes 0-15), Cr (lanes 16-31)
-// The first CTA of a frame also evaluates the rate control (K1's variance sum -> qscale) and publishes the
+// With this mapping every DC predictor (mjpegenc.c encode_block: the previous block of the same component) is
+// the neighbouring lane's DC, so prediction is one shuffle and the warps never wait for each other.  The first
+// lane of a run needs the block in front of the warp's range; its DC is recomputed from the pixels: the DC
+// output of ff_fdct_sse2 is exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17
+// == S), so eight lanes add one pixel row each -- no second FDCT.
+//
+// The tile image (h2j_common.cuh) is assembled in one of two shared-memory buffers and leaves with a single bulk
+// (TMA) store; the only CTA-wide barrier per tile is the one in front of that store.  Pixel rows of the next
+// tile are requested before the statistics of the current one are taken, so their latency is covered by work.
+//
+// The first CTA of a frame also publishes the rate-control result (K1's variance sum -> qscale) and the
 // quantiser tables; every CTA recomputes them for itself (64 threads, a few dozen instructions) instead of
 // waiting for a separate set-up launch.
-//
-// DC prediction needs the previous MCU's Y3/Cb/Cr DC levels.  Inside a tile they come from shared memory; for
-// the first MCU of a CTA's first tile they are recomputed from the pixels: the DC output of ff_fdct_sse2 is
-// exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17 == S), so no second FDCT
-// is needed.
 #pragma once
 #include "h2j_common.cuh"
 
 namespace h2j {
-
-__device__ __forceinline__ void load_block_pixels(const uint8_t *__restrict__ P, int pitch, int pw, int ph, int bx, int by,
-                                                  bool fast, const uint8_t *lut, int (&v)[64])
-{
-    if (fast && bx + 8 <= pw) {
-        uint2 rows[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = min(by + r, ph - 1);
-            rows[r] = ldg64(P + (long long)y * pitch + bx);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            v[r * 8 + 0] = rows[r].x & 0xff;
-            v[r * 8 + 1] = (rows[r].x >> 8) & 0xff;
-            v[r * 8 + 2] = (rows[r].x >> 16) & 0xff;
-            v[r * 8 + 3] = rows[r].x >> 24;
-            v[r * 8 + 4] = rows[r].y & 0xff;
-            v[r * 8 + 5] = (rows[r].y >> 8) & 0xff;
-            v[r * 8 + 6] = (rows[r].y >> 16) & 0xff;
-            v[r * 8 + 7] = rows[r].y >> 24;
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = min(by + r, ph - 1);
-            const uint8_t *row = P + (long long)y * pitch;
-#pragma unroll
-            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(bx + c, pw - 1)];
-        }
-    }
-    if (lut) {
-#pragma unroll
-        for (int i = 0; i < 64; i++) v[i] = lut[v[i]];
-    }
-}
 
 // plane / position of block n (0..3 luma, 4 Cb, 5 Cr) of MCU m
 struct BlockGeom {
@@ -73,23 +42,95 @@ __device__ __forceinline__ BlockGeom block_geom(const uint8_t *base, const Frame
     return g;
 }
 
-__global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
-                                                                  FrameState *__restrict__ state,
-                                                                  const uint8_t *__restrict__ qscale_lut,
-                                                                  FrameTab *__restrict__ tabs,
-                                                                  uint32_t *__restrict__ images,          // [frame][images_cap] tile images
-                                                                  unsigned long long *__restrict__ masks, // [frame][blocks_cap]
-                                                                  long long images_cap, long long blocks_cap, int tiles_per_cta)
+// The pixel rows a thread has in flight for its block of the coming tile.
+struct BlockFetch {
+    uint2 rows[8];
+    uint2 prow;          // lanes that help with a predecessor DC: one row of that block
+    BlockGeom g, pg;
+    bool valid;          // the block exists
+    bool fast;           // rows[] hold the pixels (aligned, not cut by the right edge); else they are read bytewise
+    bool phelp, pfast;   // this lane adds a row of the predecessor block / prow holds it
+    int prow_idx;
+};
+
+__device__ __forceinline__ void fetch_issue(BlockFetch &F, const uint8_t *base, const FrameLayout &L, int m, int n, bool valid,
+                                            bool phelp, int pm, int pn, int prow_idx)
 {
-    __shared__ __align__(16) uint32_t s_img[kTileImageWords];
+    F.valid = valid;
+    F.fast = false;
+    F.phelp = phelp;
+    F.pfast = false;
+    F.prow_idx = prow_idx;
+    if (valid) {
+        F.g = block_geom(base, L, m, n);
+        F.fast = L.aligned8 != 0 && F.g.bx + 8 <= F.g.pw;
+        if (F.fast) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) F.rows[r] = ldg64(F.g.P + (long long)min(F.g.by + r, F.g.ph - 1) * F.g.pitch + F.g.bx);
+        }
+    }
+    if (phelp) {
+        F.pg = block_geom(base, L, pm, pn);
+        F.pfast = L.aligned8 != 0 && F.pg.bx + 8 <= F.pg.pw;
+        if (F.pfast) F.prow = ldg64(F.pg.P + (long long)min(F.pg.by + prow_idx, F.pg.ph - 1) * F.pg.pitch + F.pg.bx);
+    }
+}
+
+__device__ __forceinline__ void fetch_consume(const BlockFetch &F, const uint8_t *lut, int (&v)[64])
+{
+    if (F.fast) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            v[r * 8 + 0] = F.rows[r].x & 0xff;
+            v[r * 8 + 1] = (F.rows[r].x >> 8) & 0xff;
+            v[r * 8 + 2] = (F.rows[r].x >> 16) & 0xff;
+            v[r * 8 + 3] = F.rows[r].x >> 24;
+            v[r * 8 + 4] = F.rows[r].y & 0xff;
+            v[r * 8 + 5] = (F.rows[r].y >> 8) & 0xff;
+            v[r * 8 + 6] = (F.rows[r].y >> 16) & 0xff;
+            v[r * 8 + 7] = F.rows[r].y >> 24;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint8_t *row = F.g.P + (long long)min(F.g.by + r, F.g.ph - 1) * F.g.pitch;
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(F.g.bx + c, F.g.pw - 1)];
+        }
+    }
+    if (lut) {
+#pragma unroll
+        for (int i = 0; i < 64; i++) v[i] = lut[v[i]];
+    }
+}
+
+// this lane's share (one pixel row) of the predecessor block's sample sum
+__device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const uint8_t *lut)
+{
+    if (!F.phelp) return 0;
+    if (F.pfast && !lut) return (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
+    const uint8_t *row = F.pg.P + (long long)min(F.pg.by + F.prow_idx, F.pg.ph - 1) * F.pg.pitch;
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int p = row[min(F.pg.bx + c, F.pg.pw - 1)];
+        s += lut ? lut[p] : p;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kFdctThreads, 5) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
+                                                                     FrameState *__restrict__ state,
+                                                                     const uint8_t *__restrict__ qscale_lut,
+                                                                     FrameTab *__restrict__ tabs,
+                                                                     uint32_t *__restrict__ images,  // [frame][images_cap] tile images
+                                                                     long long images_cap, int tiles_per_cta)
+{
+    __shared__ __align__(128) uint32_t s_img[2][kTileImageWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
     __shared__ unsigned int s_hist[2][256];
     __shared__ unsigned int s_dchist[2][16];
-    __shared__ int s_dc[kTileBlocks];
-    __shared__ unsigned long long s_mask[kTileBlocks];
-    __shared__ int s_prev[3];        // DC levels of the MCU in front of the current tile: Y3, Cb, Cr
-    __shared__ int s_psum[3];
     __shared__ int s_qs;
 
     const int f = blockIdx.y;
@@ -98,6 +139,26 @@ __global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t 
     const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
     const int tile0 = blockIdx.x * tiles_per_cta;
     if (tile0 >= n_tiles) return;
+    const int tile_end = min(tile0 + tiles_per_cta, n_tiles);
+
+    // lane -> block of the tile
+    const bool luma = warp < 2;
+    const int mcu_l = luma ? warp * 8 + (lane >> 2) : (lane & 15);
+    const int n = luma ? (lane & 3) : 4 + (lane >> 4);
+    const int slot = mcu_l * 6 + n;
+    const int cls = luma ? 0 : 1;
+    const uint8_t *lut = L.range_mode ? c_range_lut[cls] : nullptr;
+    // predecessor block of the warp's first lane(s): luma -> Y3 of the MCU in front of the warp's eight;
+    // chroma -> Cb (lanes 0-7 help) and Cr (lanes 8-15 help) of the MCU in front of the tile (first tile only)
+    const bool phelp_lane = luma ? lane < 8 : lane < 16;
+    const int pn = luma ? 3 : 4 + (lane >> 3);
+    const int mcu_first = luma ? warp * 8 : 0;
+
+    BlockFetch F;
+    {
+        const int m = tile0 * kTileMcus + mcu_l, pm = tile0 * kTileMcus + mcu_first - 1;
+        fetch_issue(F, base, L, m, n, m < L.n_mcu, phelp_lane && pm >= 0 && pm < L.n_mcu, pm, pn, lane & 7);
+    }
 
     // ---- rate control + quantiser set-up (ratecontrol.c first I picture, mpegvideo_enc.c encode_picture) ----
     if (tid == 0) {
@@ -107,9 +168,9 @@ __global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t 
         else {
             // predict_size(): the IEEE-exact part; the pow()/rounding tail is folded into qscale_lut by the host
             const double bits = __ddiv_rn(__dmul_rn(826.0, sqrt((double)var)), 236.0);
-            int n = (int)bits;
-            n = n > kQscaleLutSize - 1 ? kQscaleLutSize - 1 : (n < 0 ? 0 : n);
-            q = qscale_lut[n];
+            int nb = (int)bits;
+            nb = nb > kQscaleLutSize - 1 ? kQscaleLutSize - 1 : (nb < 0 ? 0 : nb);
+            q = qscale_lut[nb];
         }
         s_qs = q;
         if (blockIdx.x == 0) {
@@ -118,7 +179,6 @@ __global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t 
             tabs[f].status = 0;
         }
     }
-    if (tid < 3) s_psum[tid] = 0;
     for (int i = tid; i < 512; i += kFdctThreads) (&s_hist[0][0])[i] = 0;
     if (tid < 32) (&s_dchist[0][0])[tid] = 0;
     __syncthreads();
@@ -137,78 +197,74 @@ __global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t 
             tabs[f].dqt_zz[tid] = mk;
         }
     }
-    // ---- predictor DCs in front of the CTA's first tile: pixel sums of Y3/Cb/Cr of the previous MCU ----
-    if (tile0 > 0 && tid < 24) {
-        const int which = tid >> 3, r = tid & 7;  // 0: Y3, 1: Cb, 2: Cr
-        const BlockGeom g = block_geom(base, L, tile0 * kTileMcus - 1, which == 0 ? 3 : 3 + which);
-        const uint8_t *lutp = L.range_mode ? c_range_lut[which ? 1 : 0] : nullptr;
-        const uint8_t *row = g.P + (long long)min(g.by + r, g.ph - 1) * g.pitch;
-        int s = 0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const int p = row[min(g.bx + c, g.pw - 1)];
-            s += lutp ? lutp[p] : p;
-        }
-        atomicAdd(&s_psum[which], s);
-    }
     __syncthreads();
-    if (tid < 3) s_prev[tid] = tile0 > 0 ? quant_dc(s_psum[tid]) : 128;  // 128 = the encoder's initial last_dc (1024 >> 3)
-    // (visibility of s_prev is covered by the barrier in front of its first use below)
 
-    const int mcu_l = warp < 2 ? (lane >> 1) : (lane & 15);
-    const int n = warp < 2 ? (warp * 2 + (lane & 1)) : (4 + (lane >> 4));
-    const int slot = mcu_l * 6 + n;
-    const int cls = n < 4 ? 0 : 1;
-    const uint8_t *lut = L.range_mode ? c_range_lut[cls] : nullptr;
-    int16_t *img16 = reinterpret_cast<int16_t *>(s_img);
+    int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
 
-    for (int t = 0; t < tiles_per_cta; t++) {
-        const int tile = tile0 + t;
-        if (tile >= n_tiles) break;
-        const int m = tile * kTileMcus + mcu_l;
-        const bool valid = m < L.n_mcu;
+    for (int tile = tile0; tile < tile_end; tile++) {
+        uint32_t *img = s_img[(tile - tile0) & 1];
+        const bool valid = F.valid;
+
+        // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
+        int psum = fetch_pred_rowsum(F, lut);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+        psum += __shfl_xor_sync(0xffffffffu, psum, 4);
+        const int psum_cr = __shfl_sync(0xffffffffu, psum, 8);  // chroma: lanes 8-15 summed Cr
+        const int pm = tile * kTileMcus + mcu_first - 1;
+        int pred_first;  // meaningful in lane 0 (and lane 16 of the chroma warp)
+        if (luma) pred_first = pm >= 0 ? quant_dc(psum) : 128;  // 128 = the encoder's initial last_dc (1024 >> 3)
+        else if (tile == tile0) pred_first = pm >= 0 ? quant_dc(lane < 16 ? psum : psum_cr) : 128;
+        else pred_first = chroma_carry;
+
         unsigned mask_lo = 0, mask_hi = 0;
         uint32_t word0_hi = 0;
         int dc = 0;
+        uint32_t *rec = img + slot * kBlkWords;
         if (valid) {
-            const BlockGeom g = block_geom(base, L, m, n);
             int v[64];
-            load_block_pixels(g.P, g.pitch, g.pw, g.ph, g.bx, g.by, L.aligned8 != 0, lut, v);
+            fetch_consume(F, lut, v);
             fdct_8x8(v);
             dc = quant_dc(v[0]);
+            // quantise without the final >> 16: the level is the upper half of the 32-bit product, so two of them
+            // are packed into one record word with a single byte permute
 #pragma unroll
-            for (int i = 1; i < 64; i++) v[i] = quant_ac2(v[i], s_q[i], s_bq[i]);
+            for (int i = 1; i < 64; i++) v[i] = quant_ac2_hi(v[i], s_q[i], s_bq[i]);
             // zigzag; word j of the record holds levels j (low half) and j + 32 (high half), so that the non-zero
             // flags of 32 levels fall out of 16 packed min(x, 1) results shifted into place (VIMNMX.U16x2)
-            uint32_t *dst = s_img + slot * kBlkWords;
             unsigned fa = 0, fb = 0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                const uint32_t w = (uint32_t)(v[zz_of(j)] & 0xffff) | ((uint32_t)v[zz_of(j + 32)] << 16);
+                const uint32_t w = j == 0 ? __byte_perm(0u, (uint32_t)v[zz_of(32)], 0x7610) : __byte_perm((uint32_t)v[zz_of(j)], (uint32_t)v[zz_of(j + 32)], 0x7632);
                 const unsigned t = __vminu2(w, 0x00010001u);
                 if (j < 16) fa += t << j;
                 else fb += t << (j - 16);
-                if (j == 0) word0_hi = w & 0xffff0000u;  // the low half becomes the DC difference below
-                else dst[j] = w;
+                if (j == 0) word0_hi = w;  // the low half becomes the DC difference below
+                else rec[j] = w;
             }
             mask_lo = ((fa & 0xffffu) | (fb << 16)) & ~1u;  // bit 0 is the DC position: always coded, never in the mask
             mask_hi = (fa >> 16) | (fb & 0xffff0000u);
+            rec[kMaskLoWord] = mask_lo;
+            img[kMaskHiOff + slot] = mask_hi;
         }
-        s_dc[slot] = dc;
-        s_mask[slot] = ((unsigned long long)mask_hi << 32) | mask_lo;
-        __syncthreads();
 
+        // ---- request the next tile's pixels: nothing of this tile's 64-value block is live any more ----
+        if (tile + 1 < tile_end) {
+            const int m = (tile + 1) * kTileMcus + mcu_l, pmn = (tile + 1) * kTileMcus + mcu_first - 1;
+            fetch_issue(F, base, L, m, n, m < L.n_mcu, luma && phelp_lane && pmn < L.n_mcu, pmn, pn, lane & 7);
+        }
+
+        // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
+        const int up = __shfl_up_sync(0xffffffffu, dc, 1);
+        const int pred = (luma ? lane == 0 : (lane & 15) == 0) ? pred_first : up;
+        const int last = __shfl_sync(0xffffffffu, dc, (lane & 16) | 15);  // chroma: this tile's last Cb / Cr
+        chroma_carry = last;
         if (valid) {
-            // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
-            int pred;
-            if (n >= 1 && n <= 3) pred = s_dc[slot - 1];
-            else if (n == 0) pred = mcu_l > 0 ? s_dc[slot - 3] : s_prev[0];
-            else pred = mcu_l > 0 ? s_dc[slot - 6] : s_prev[n - 3];
             const int diff = dc - pred;
-            s_img[slot * kBlkWords] = (uint32_t)(diff & 0xffff) | word0_hi;
+            rec[0] = (uint32_t)(diff & 0xffff) | word0_hi;
             atomicAdd(&s_dchist[cls][mag_bits(diff)], 1u);
             // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
-            const int16_t *lv = img16 + slot * kBlkHalf;
+            const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
             unsigned int *hist = s_hist[cls];
             int prev = 0;
 #pragma unroll
@@ -226,21 +282,14 @@ __global__ void __launch_bounds__(kFdctThreads) fdct_quant_kernel(const uint8_t 
             }
             if (prev < 63) atomicAdd(&hist[0], 1u);
         }
-        __syncthreads();
 
-        // ---- contiguous copy-out: the tile image (128-bit stores) and the masks ----
-        const int blocks_here = min(kTileBlocks, L.n_blocks - tile * kTileBlocks);
-        {
-            uint4 *gdst = reinterpret_cast<uint4 *>(images + ((long long)f * images_cap + tile) * kTileImageWords);
-            const uint4 *ssrc = reinterpret_cast<const uint4 *>(s_img);
-            const int n16 = (blocks_here * kBlkWords * 4 + 15) >> 4;
-            for (int c = tid; c < n16; c += kFdctThreads) gdst[c] = ssrc[c];
-        }
-        if (tid < blocks_here) masks[(long long)f * blocks_cap + (long long)tile * kTileBlocks + tid] = s_mask[tid];
-        // the last MCU of this tile predicts the first of the next
-        if (tid < 3) s_prev[tid] = s_dc[(kTileMcus - 1) * 6 + 3 + tid];
+        // ---- the image leaves with one bulk store; the other buffer's store must have been read out by now ----
+        fence_proxy_async_smem();
+        if (tid == 0) bulk_wait_read_all();
         __syncthreads();
+        if (tid == 0) bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords, img, kTileImageBytes);
     }
+    if (tid == 0) bulk_wait_all();
 
     for (int i = tid; i < 512; i += kFdctThreads) {
         const unsigned c = (&s_hist[0][0])[i];

@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(128) convert_pad_kernel(const uint8_t *__restr
     unsigned w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 16; k++) w[k >> 2] |= (unsigned)s_lut[px[k]] << (8 * (k & 3));
-    *reinterpret_cast<uint4 *>(O + (long long)y * padw + x0) = make_uint4(w[0], w[1], w[2], w[3]);
+    // padded chroma rows are only 8-byte aligned (padw = mcu_w * 8): two 64-bit stores
+    uint2 *o2 = reinterpret_cast<uint2 *>(O + (long long)y * padw + x0);
+    o2[0] = make_uint2(w[0], w[1]);
+    if (x0 + 8 < padw) o2[1] = make_uint2(w[2], w[3]);
 }
 
 }  // namespace h2j

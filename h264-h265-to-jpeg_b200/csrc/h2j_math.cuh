@@ -104,6 +104,12 @@ H2J_HD int quant_ac2(int x, int q, int bq)
     const int c = bq ^ (s & 0xffff);       // bq or 65535 - bq
     return (x * q + c) >> 16;
 }
+// the same product before the final shift: the level is its upper 16 bits (|level| < 2^15 for FDCT outputs)
+H2J_HD int quant_ac2_hi(int x, int q, int bq)
+{
+    const int s = x >> 31;
+    return x * q + (bq ^ (s & 0xffff));
+}
 H2J_HD int quant_ac(int x, uint32_t packed) { return quant_ac2(x, (int)(packed & 0xffffu), (int)(packed >> 16)); }
 // DC: ((block[0] >> 2) + q) * ff_inverse[2q] >> 32 with q = 8  ==  ((x >> 2) + 8) >> 4  (x >= 0)
 H2J_HD int quant_dc(int x) { return ((x >> 2) + 8) >> 4; }
