@@ -70,7 +70,7 @@ struct h2j_encoder {
     int tiles_cap = 0;            // K4 tiles per frame at max geometry
     int chunks_cap = 0;           // K5 chunks per frame
     int stuff_ctas = 32;          // K5 CTAs per frame
-    int fdct_tiles_per_cta = 8;   // consecutive K2 tiles one CTA walks (amortises its set-up and histogram flush)
+    int fdct_tiles_per_cta = 16;  // upper bound of consecutive K2 tiles one CTA walks
     size_t frame_bytes_cap = 0;
     uint8_t *d_qscale_lut = nullptr;
     char *d_comment = nullptr;
@@ -213,7 +213,11 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
     {
         ScopedTiming t(e, sl, "fdct_quant_kernel");
-        const int tiles_per_cta = e->fdct_tiles_per_cta;
+        // consecutive tiles per CTA: as many as keep the grid at four waves or more (amortises the per-CTA set-up
+        // and histogram flush), at most 16
+        int tiles_per_cta = (int)((long long)n_tiles * n / ((long long)e->sm_count * 5 * 4));
+        tiles_per_cta = tiles_per_cta < 1 ? 1 : (tiles_per_cta > e->fdct_tiles_per_cta ? e->fdct_tiles_per_cta : tiles_per_cta);
+        if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
         fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, 0, st>>>(
             d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
@@ -249,7 +253,7 @@ int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
     cudaStream_t st = sl.stream;
     {
         ScopedTiming t(e, sl, "pack_offsets_kernel");
-        pack_offsets_kernel<<<1, 32, 0, st>>>(sl.d_tabs, sl.n, (long long)e->out_cap, sl.d_offsets, sl.d_status);
+        pack_offsets_kernel<<<1, kPackOffsetsThreads, 0, st>>>(sl.d_tabs, sl.n, (long long)e->out_cap, sl.d_offsets, sl.d_status);
         e->launches++;
     }
     sl.packed = pack;

@@ -23,6 +23,8 @@
 //   tail word    [63] valid   [30:0] the tile's last 31 bits (every tile but a frame's last is longer than that:
 //                192 blocks of at least two bits each)
 #pragma once
+#include <cstddef>
+
 #include "h2j_common.cuh"
 
 namespace h2j {
@@ -181,7 +183,9 @@ __device__ __forceinline__ bool store_run(const unsigned int *s_bits, unsigned P
     return overflow;
 }
 
-constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + (kEntWinWords + 4) * 4;
+constexpr int kEntTabBytes = (2 * 16 + 2 * 256) * 4;  // DC luma/chroma (16 entries each), AC luma/chroma of FrameTab::hcode
+constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + kEntTabBytes + (kEntWinWords + 4) * 4;
+static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0, "hcode must be bulk-copyable");
 constexpr int kEntPreZeroWords = 768;  // cleared while the bulk load is in flight; covers 128 bits per block
 
 __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
@@ -193,9 +197,9 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
 {
     extern __shared__ __align__(128) unsigned char ent_smem[];
     uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                   // two tile images
-    unsigned int *s_bits = reinterpret_cast<unsigned int *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [0] guard, [1..] bits
-    __shared__ uint32_t s_hdc[2][16];
-    __shared__ uint32_t s_hac[2][256];
+    uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [2][16] DC code tables
+    uint32_t *s_hac = s_hdc + 32;                                                                // [2][256] AC code tables
+    unsigned int *s_bits = reinterpret_cast<unsigned int *>(ent_smem + kEntFdctTiles * kTileImageBytes + kEntTabBytes);  // [0] guard, [1..] bits
     __shared__ unsigned s_warp[kEntThreads / 32];
     __shared__ unsigned s_ticket;
     __shared__ unsigned s_excl_len;
@@ -206,19 +210,19 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         s_ticket = atomicAdd(ticket, 1u);
         mbar_init(&s_bar, 1);
     }
+    for (int i = tid; i < kEntPreZeroWords; i += kEntThreads) s_bits[i] = 0;  // while the ticket is on its way
     __syncthreads();
     const int f = (int)(s_ticket / (unsigned)tiles_per_frame);
     const int tile = (int)(s_ticket % (unsigned)tiles_per_frame);
     if (tid == 0) {
         // images_cap is even, so both images of the tile exist in the buffer even when the second holds no block
         const uint32_t *src = images + ((long long)f * images_cap + (long long)tile * kEntFdctTiles) * kTileImageWords;
-        mbar_expect_tx(&s_bar, kEntFdctTiles * kTileImageBytes);
+        mbar_expect_tx(&s_bar, kEntFdctTiles * kTileImageBytes + kEntTabBytes);
         bulk_g2s(s_img, src, kEntFdctTiles * kTileImageBytes, &s_bar);
+        bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
+        bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
+        bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
     }
-    const FrameTab *T = tabs + f;
-    for (int i = tid; i < 512; i += kEntThreads) (&s_hac[0][0])[i] = T->hcode[2 + (i >> 8)][i & 255];
-    if (tid < 32) (&s_hdc[0][0])[tid] = T->hcode[tid >> 4][tid & 15];
-    for (int i = tid; i < kEntPreZeroWords; i += kEntThreads) s_bits[i] = 0;
 
     const int b = tile * kEntBlocks + tid;
     const bool valid = b < L.n_blocks;
@@ -226,8 +230,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
     const uint32_t *rec = s_img + img_i * kTileImageWords + rec_i * kBlkWords;
     const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
     const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
-    __syncthreads();      // tables in shared memory
-    mbar_wait(&s_bar, 0); // coefficient images landed
+    mbar_wait(&s_bar, 0); // coefficient images and code tables landed
     unsigned mask_lo = 0, mask_hi = 0;
     if (valid) {
         mask_lo = rec[kMaskLoWord];
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
 
     // ---- 1. lengths ----
     unsigned len = 0;
-    if (valid) len = walk_block<false, BitSink>(cb, mask_lo, mask_hi, s_hdc[cls], s_hac[cls], nullptr);
+    if (valid) len = walk_block<false, BitSink>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, nullptr);
     unsigned incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         if (valid) {
             BitSink sink;
             sink.init(s_bits + 1, off);
-            walk_block<true, BitSink>(cb, mask_lo, mask_hi, s_hdc[cls], s_hac[cls], &sink);
+            walk_block<true, BitSink>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
             sink.flush();
         }
         __syncthreads();
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         if (valid && off + len > lo) {
             BitSinkClip sink;
             sink.init(s_bits + 1, off, lo, tile_len);
-            walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc[cls], s_hac[cls], &sink);
+            walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
         }
         __syncthreads();
         own_tail = s_bits[2] & 0x7fffffffu;
@@ -317,14 +320,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         }
         if (lane == 0) {
             if (tile > 0) st_desc(&D[tile], desc_pack(2, excl + tile_len));
-            unsigned tail_in = 0;
-            if (tile > 0 && (excl & 31)) {
-                unsigned long long t;
-                do { t = ld_desc(&TW[tile - 1]); } while ((t >> 63) == 0);
-                tail_in = (unsigned)t & 0x7fffffffu;
-            }
             s_excl_len = excl;
-            s_bits[0] = tail_in;  // bits of the tile in front living in our first word
             if (tile == tiles_per_frame - 1) state[f].scan_bits = (unsigned long long)excl + tile_len;
         }
     }
@@ -332,6 +328,17 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
 
     // ---- 4. shift to the global bit position, store, count 0xFF bytes ----
     const unsigned P = s_excl_len;
+    // Only the tile's first output word needs bits of the tile in front, and only thread 0 builds that word: it alone
+    // waits for the neighbour's tail, everybody else is already storing.
+    if (tid == 0) {
+        unsigned tail_in = 0;
+        if (tile > 0 && (P & 31)) {
+            unsigned long long t;
+            do { t = ld_desc(&TW[tile - 1]); } while ((t >> 63) == 0);
+            tail_in = (unsigned)t & 0x7fffffffu;
+        }
+        s_bits[0] = tail_in;
+    }
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
     const bool last_tile = tile == tiles_per_frame - 1;
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
     if (!windowed) {
         overflow = store_run(s_bits, P, tile_len, last_tile, gs, scan_cap_words, cff, tid);
     } else {
+        __syncthreads();
         unsigned tail_in = s_bits[0];
         for (unsigned lo = 0; lo < tile_len; lo += kEntWinBits) {
             const unsigned hi = min(lo + (unsigned)kEntWinBits, tile_len);
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
             if (valid && off < hi && off + len > lo) {
                 BitSinkClip sink;
                 sink.init(s_bits + 1, off, lo, hi);
-                walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc[cls], s_hac[cls], &sink);
+                walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
             }
             if (tid == 0) s_bits[0] = tail_in;
             __syncthreads();

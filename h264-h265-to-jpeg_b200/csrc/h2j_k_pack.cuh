@@ -8,21 +8,45 @@ namespace h2j {
 // K6: pack the JPEGs of a batch back to back (so one D2H copy moves exactly the bytes produced).
 // offsets[n+1] is computed by block 0 of pack_offsets_kernel.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_offsets_kernel(const FrameTab *__restrict__ tabs, int n, long long out_cap, unsigned long long *__restrict__ offsets,
-                                    int *__restrict__ status)
+constexpr int kPackOffsetsThreads = 256;
+__global__ void __launch_bounds__(kPackOffsetsThreads) pack_offsets_kernel(const FrameTab *__restrict__ tabs, int n, long long out_cap,
+                                                                           unsigned long long *__restrict__ offsets, int *__restrict__ status)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long acc = 0;
-        for (int i = 0; i < n; i++) {
-            offsets[i] = acc;
+    // one CTA: exclusive scan of the JPEG sizes, a chunk of kPackOffsetsThreads frames at a time
+    __shared__ unsigned long long s_warp[kPackOffsetsThreads / 32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kPackOffsetsThreads) {
+        const int i = i0 + tid;
+        unsigned long long sz = 0;
+        if (i < n) {
             const int st = tabs[i].status;
             status[i] = st;
-            long long sz = tabs[i].jpeg_bytes;
-            if (st != 0 || sz > out_cap) sz = 0;
-            acc += (unsigned long long)sz;
+            const long long b = tabs[i].jpeg_bytes;
+            sz = (st != 0 || b > out_cap) ? 0ull : (unsigned long long)b;
         }
-        offsets[n] = acc;
+        unsigned long long incl = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_base, total = 0;
+#pragma unroll
+        for (int w = 0; w < kPackOffsetsThreads / 32; w++) {
+            if (w < warp) off += s_warp[w];
+            total += s_warp[w];
+        }
+        if (i < n) offsets[i] = off + incl - sz;
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
     }
+    if (tid == 0) offsets[n] = s_base;
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ out, long long out_cap,

@@ -17,7 +17,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libh2j_b200.so")
+# H2J_B200_LIB selects another build of the same library (kernel tuning experiments); there is still no fallback.
+LIB_PATH = os.environ.get("H2J_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libh2j_b200.so")
 
 OK = 0
 ERR_INVALID_ARG = -1
