@@ -33,9 +33,12 @@ struct Slot {
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
-    unsigned long long *d_descs = nullptr;
+    unsigned long long *d_descs = nullptr;   // K4b group descriptors
     unsigned int *d_ticket = nullptr;
+    unsigned int *d_stage_alloc = nullptr;   // K4a: staging words handed out per frame
     unsigned int *d_chunk_ff = nullptr;
+    uint32_t *d_stage = nullptr;             // K4a -> K4b: the units' bits, word aligned, any order
+    unsigned long long *d_unit_info = nullptr;
     FrameTab *d_tabs = nullptr;
     uint32_t *d_scan = nullptr;
     uint8_t *d_out = nullptr;
@@ -68,6 +71,9 @@ struct h2j_encoder {
     long long images_cap = 0;     // K2 tile images per frame at max geometry, rounded up to whole K4 tiles
     long long blocks_cap = 0;     // images_cap * 96
     int tiles_cap = 0;            // K4 tiles per frame at max geometry
+    int units_cap = 0;            // K4 units (32 blocks) per frame
+    int groups_cap = 0;           // K4b groups (64 units) per frame
+    long long stage_cap_words = 0;
     int chunks_cap = 0;           // K5 chunks per frame
     int stuff_ctas = 32;          // K5 CTAs per frame
     int fdct_tiles_per_cta = 16;  // upper bound of consecutive K2 tiles one CTA walks
@@ -230,10 +236,18 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     }
     const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
-        ScopedTiming t(e, sl, "entropy_kernel");
-        entropy_kernel<<<tiles_per_frame * n, kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_state, sl.d_images, e->images_cap, sl.d_descs,
-                                                                               sl.d_ticket, tiles_per_frame, sl.d_scan, e->scan_cap_words,
-                                                                               sl.d_chunk_ff, e->chunks_cap);
+        ScopedTiming t(e, sl, "entropy_walk_kernel");
+        entropy_walk_kernel<<<dim3(tiles_per_frame, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info,
+                                                                                         e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        e->launches++;
+    }
+    {
+        ScopedTiming t(e, sl, "scan_place_kernel");
+        const int n_units = (L.n_blocks + kUnitBlocks - 1) / kUnitBlocks;
+        const int groups_per_frame = (n_units + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
+        scan_place_kernel<<<groups_per_frame * n, kPlaceThreads, 0, st>>>(L, sl.d_tabs, sl.d_state, sl.d_unit_info, e->units_cap, sl.d_stage,
+                                                                         e->stage_cap_words, sl.d_descs, groups_per_frame, sl.d_ticket, sl.d_scan,
+                                                                         e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
         e->launches++;
     }
     {
@@ -279,7 +293,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_zero);
+    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -387,6 +401,9 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->images_cap = ((n_mcu + kTileMcus - 1) / kTileMcus + kEntFdctTiles - 1) / kEntFdctTiles * kEntFdctTiles;
     e->blocks_cap = e->images_cap * kTileBlocks;
     e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
+    e->units_cap = e->tiles_cap * kEntWarps;
+    e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
+    e->stage_cap_words = e->scan_cap_words + e->units_cap;  // every unit starts on a word: at most one word of slack each
     e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
     e->frame_bytes_cap = align_up(tight_frame_bytes(s->max_width, s->max_height), 256);
 
@@ -403,7 +420,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
     CUB(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
-    CUB(cudaFuncSetAttribute(entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
+    CUB(cudaFuncSetAttribute(entropy_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
 
     const int B = s->max_batch;
     e->slots.resize(s->n_slots);
@@ -414,14 +431,18 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
         CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
-        const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->tiles_cap * 2 * B, 256);  // length + tail word per tile
+        const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->groups_cap * B, 256);
+        const size_t alloc_bytes = align_up(sizeof(unsigned int) * (size_t)B, 256);
         const size_t chunk_bytes = align_up(sizeof(unsigned int) * (size_t)e->chunks_cap * B, 256);
-        sl.zero_bytes = state_bytes + desc_bytes + 256 + chunk_bytes;
+        sl.zero_bytes = state_bytes + desc_bytes + 256 + alloc_bytes + chunk_bytes;
         CUB(cudaMalloc(&sl.d_zero, sl.zero_bytes));
         sl.d_state = reinterpret_cast<FrameState *>(sl.d_zero);
         sl.d_descs = reinterpret_cast<unsigned long long *>(sl.d_zero + state_bytes);
         sl.d_ticket = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes);
-        sl.d_chunk_ff = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes + 256);
+        sl.d_stage_alloc = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes + 256);
+        sl.d_chunk_ff = reinterpret_cast<unsigned int *>(sl.d_zero + state_bytes + desc_bytes + 256 + alloc_bytes);
+        CUB(cudaMalloc(&sl.d_stage, (size_t)e->stage_cap_words * 4 * B));
+        CUB(cudaMalloc(&sl.d_unit_info, sizeof(unsigned long long) * (size_t)e->units_cap * B));
         CUB(cudaMalloc(&sl.d_tabs, sizeof(FrameTab) * B));
         CUB(cudaMalloc(&sl.d_scan, (size_t)e->scan_cap_words * 4 * B));
         CUB(cudaMalloc(&sl.d_out, e->out_cap * B));

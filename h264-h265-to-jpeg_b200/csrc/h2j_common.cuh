@@ -56,8 +56,6 @@ constexpr int kFdctThreads = kTileBlocks;
 constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
 constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192
 constexpr int kEntThreads = kEntBlocks;
-constexpr int kEntWinWords = 2048;                          // shared-memory bit window: 8 KiB = 65536 bits
-constexpr int kEntWinBits = kEntWinWords * 32;
 constexpr int kMaxBitsPerBlock = 27 * 64;                   // DC (16+11) + 63 * (16+11); ZRLs only replace coefficients
 
 constexpr int kHuffGroup = 128;                             // threads per table

@@ -1,27 +1,26 @@
-// K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame).
+// K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame), in two kernels.
 //
-// A tile is 192 consecutive blocks of one frame (two K2 tile images).  One elected thread pulls the images (levels
-// and non-zero masks) into shared memory with a single bulk copy (cp.async.bulk -> SASS UBLKCP) signalled on an
-// mbarrier while the other threads fetch the frame's code tables and clear the bit window.
-//   1. every thread walks the non-zero mask of its block and sums code lengths; block-wide exclusive scan.  The
-//      tile's bit length is published at once, and warp 0 issues its look-back loads (tiles are handed out through
-//      an atomic ticket, so every predecessor is already running).
-//   2. threads emit their codes into the tile's shared-memory bit window.
-//   3. warp 0 publishes the tile's trailing 31 bits, resolves the exclusive prefix from the loads issued in 1
-//      (decoupled look-back; by now the predecessors have long published their lengths) and fetches the trailing
-//      bits of the tile in front -- the only thing that depends on a neighbour's emission.
-//   4. the window is shifted to the tile's global bit position and stored as big-endian words; a 32-bit word is
-//      written by the tile that holds its last bit, with the bits of the tile in front taken from its published
-//      tail -- no atomics on the scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are
-//      counted into per-chunk counters for K5.
-// The bit window holds 64 Kibit.  A tile that needs more (> 341 bits per block on average; the reference's own
-// 2 MiB output cap is hit first at 1080p) takes the windowed path: the same emission clipped to one window of the
-// tile's bit range at a time.
+// K4a entropy_walk_kernel -- all the coding work, no dependency between CTAs or warps:
+//   A CTA takes a tile of 192 consecutive blocks of one frame (two K2 tile images) and pulls the images (levels
+//   and non-zero masks) and the frame's code tables into shared memory with bulk copies (cp.async.bulk -> SASS
+//   UBLKCP) signalled on an mbarrier.  Each of the six warps then works alone on its UNIT of 32 blocks:
+//     1. ONE walk over the block: every lane encodes its block into a private 256-bit slot in shared memory and
+//        learns its bit length on the way (a block that needs more keeps counting and is emitted directly in 2);
+//        warp scan of the lengths.
+//     2. the slots are merged into the warp's bit window at the scanned offsets (a couple of shifted ORs per lane).
+//     3. the unit's bits, still starting at bit 0 of a word, go to a staging buffer at a position reserved with one
+//        atomicAdd (order does not matter), and (position, bit length) is recorded per unit.
+//   A warp window holds 8 Kibit.  A unit that needs more (> 256 bits per block on average) takes the windowed path:
+//   direct emission clipped to one window of the unit's bit range at a time.
 //
-// Descriptors (64-bit words, so a single relaxed store/load carries everything), two per tile:
-//   length word  [63:62] status (0 invalid, 1 tile length, 2 inclusive prefix length)   [31:0] bits
-//   tail word    [63] valid   [30:0] the tile's last 31 bits (every tile but a frame's last is longer than that:
-//                192 blocks of at least two bits each)
+// K4b scan_place_kernel -- turns the staged units into the frame's bit stream (0.25 MB per 1080p frame):
+//   A CTA takes a group of 64 consecutive units through an atomic ticket, scans their bit lengths, publishes the
+//   group total and resolves the group's exclusive prefix with a decoupled look-back over the frame's earlier
+//   groups (one 64-bit descriptor per group: [63:62] status 0 invalid / 1 group total / 2 inclusive prefix,
+//   [61:0] bits).  Every unit is then shifted to its global bit position and stored as big-endian words; a 32-bit
+//   word is written by the unit that holds its last bit, with the leading bits fetched from the staged unit in
+//   front.  No atomics on the scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are counted
+//   into per-chunk counters for K5; the frame's last word is padded with ones (put_bits / picture trailer).
 #pragma once
 #include <cstddef>
 
@@ -29,9 +28,9 @@
 
 namespace h2j {
 
-__device__ __forceinline__ unsigned long long desc_pack(unsigned status, unsigned len) { return ((unsigned long long)status << 62) | len; }
+__device__ __forceinline__ unsigned long long desc_pack(unsigned status, unsigned long long len) { return ((unsigned long long)status << 62) | len; }
 __device__ __forceinline__ unsigned desc_status(unsigned long long d) { return (unsigned)(d >> 62); }
-__device__ __forceinline__ unsigned desc_len(unsigned long long d) { return (unsigned)d; }
+__device__ __forceinline__ unsigned long long desc_len(unsigned long long d) { return d & 0x3fffffffffffffffull; }
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p)
 {
     unsigned long long v;
@@ -42,6 +41,22 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+constexpr int kUnitBlocks = 32;                              // one warp
+constexpr int kEntWarps = kEntThreads / 32;                  // 6 units per tile
+constexpr int kWarpWinWords = 256;                           // per-warp bit window: 8 Kibit
+constexpr int kWarpWinBits = kWarpWinWords * 32;
+constexpr int kWarpWinStride = kWarpWinWords + 4;            // spare words for the last partial OR
+constexpr int kSlotWords = 8;                                // private slot of a block: 256 bits
+constexpr int kSlotBits = kSlotWords * 32;
+constexpr int kSlotStride = kSlotWords + 1;                  // odd stride: the lanes' word i never share a bank
+constexpr int kPlaceGroupUnits = 64;                         // K4b: units per CTA
+constexpr int kPlaceThreads = 256;
+
+// per-unit record written by K4a: where the unit's bits were staged and how many there are
+__device__ __forceinline__ unsigned long long unit_pack(unsigned pos_words, unsigned bits) { return ((unsigned long long)pos_words << 32) | bits; }
+__device__ __forceinline__ unsigned unit_pos(unsigned long long r) { return (unsigned)(r >> 32); }
+__device__ __forceinline__ unsigned unit_bits(unsigned long long r) { return (unsigned)r; }
 
 // ---- bit sinks ------------------------------------------------------------------------------------
 struct BitSink {  // appends MSB-first into a zeroed shared-memory word array
@@ -88,6 +103,26 @@ struct BitSinkClip {  // same stream, but only the bits inside [lo, hi) are kept
         if ((unsigned)v) atomicOr(&buf[(r >> 5) + 1], (unsigned)v);
     }
     __device__ __forceinline__ void flush() {}
+};
+
+struct SlotSink {  // MSB-first into the lane's private slot; keeps counting (and drops the words) past its capacity
+    unsigned int *slot;
+    unsigned long long acc;
+    int fill;
+    int widx;
+    __device__ __forceinline__ void init(unsigned int *s) { slot = s; acc = 0; fill = 0; widx = 0; }
+    __device__ __forceinline__ void put(unsigned bits, int len)
+    {
+        acc = (acc << len) | bits;
+        fill += len;
+        if (fill >= 32) {
+            if (widx < kSlotWords) slot[widx] = (unsigned)(acc >> (fill - 32));
+            widx++;
+            fill -= 32;
+        }
+    }
+    __device__ __forceinline__ unsigned bits() const { return (unsigned)(widx * 32 + fill); }
+    __device__ __forceinline__ void flush() { if (fill > 0 && widx < kSlotWords) slot[widx] = (unsigned)(acc << (32 - fill)); }
 };
 
 // One pass over a block.  EMIT=false: returns the bit length.  EMIT=true: writes the bits into `sink`.
@@ -141,80 +176,29 @@ __device__ __forceinline__ unsigned walk_block(const int16_t *cb, unsigned mask_
     return total;
 }
 
-// last min(len,31) bits of a stream of `len` bits held MSB-first in words[1..]; words[0] must be readable
-__device__ __forceinline__ unsigned stream_tail(const unsigned int *words, unsigned len)
-{
-    if (len == 0) return 0;
-    const unsigned endw = (len - 1) >> 5;        // word holding the last bit
-    const unsigned used = ((len - 1) & 31) + 1;  // bits used in it
-    const unsigned long long two = ((unsigned long long)(endw ? words[endw] : 0u) << 32) | words[endw + 1];
-    const unsigned last32 = (unsigned)(two >> (32 - used));
-    return len >= 31 ? (last32 & 0x7fffffffu) : (last32 & ((1u << len) - 1u));
-}
-
-// Phase 4 for a run of `len` bits that starts at global bit position P of frame f's scan: the bits are in
-// s_bits[1..] (MSB first), s_bits[0] holds the bits in front of P (right aligned).  Words whose last bit lies in
-// the run are stored; with `final_run` the frame's last, incomplete word is stored too, padded with ones up to the
-// byte boundary (ff_mjpeg_encode_picture_trailer / put_bits padding).
-__device__ __forceinline__ bool store_run(const unsigned int *s_bits, unsigned P, unsigned len, bool final_run, uint32_t *__restrict__ gs,
-                                          long long scan_cap_words, unsigned int *__restrict__ chunk_ff, int tid)
-{
-    const unsigned s = P & 31;
-    const long long W0 = P >> 5;
-    const unsigned long long endbit = (unsigned long long)P + len;
-    long long Wend = (long long)(endbit >> 5);
-    const unsigned used = (unsigned)(endbit & 31);
-    if (final_run && used) Wend++;
-    bool overflow = false;
-    for (long long W = W0 + tid; W < Wend; W += kEntThreads) {
-        const int j = (int)(W - W0);
-        const unsigned hi = s_bits[j], lo = s_bits[j + 1];  // local words j-1 and j
-        unsigned v = s ? ((hi << (32 - s)) | (lo >> s)) : lo;
-        if (final_run && used && W == Wend - 1) {
-            const unsigned padn = (8 - (used & 7)) & 7;
-            v |= ((1u << padn) - 1u) << (32 - used - padn);
-        }
-        if (W < scan_cap_words) {
-            gs[W] = __byte_perm(v, 0, 0x0123);
-            const unsigned c = count_ff_bytes(v);
-            if (c) atomicAdd(&chunk_ff[W >> kChunkShift], c);
-        } else overflow = true;
-    }
-    return overflow;
-}
-
 constexpr int kEntTabBytes = (2 * 16 + 2 * 256) * 4;  // DC luma/chroma (16 entries each), AC luma/chroma of FrameTab::hcode
-constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + kEntTabBytes + (kEntWinWords + 4) * 4;
+constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + kEntTabBytes + kEntWarps * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
 static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0, "hcode must be bulk-copyable");
-constexpr int kEntPreZeroWords = 768;  // cleared while the bulk load is in flight; covers 128 bits per block
 
-__global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
-                                                              const uint32_t *__restrict__ images, long long images_cap,
-                                                              unsigned long long *__restrict__ descs,  // [frame][2][tiles_per_frame]
-                                                              unsigned int *__restrict__ ticket, int tiles_per_frame,
-                                                              uint32_t *__restrict__ scan, long long scan_cap_words,
-                                                              unsigned int *__restrict__ chunk_ff, int chunks_cap)
+// grid (tiles_per_frame, frames)
+__global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L, FrameTab *__restrict__ tabs,
+                                                                   const uint32_t *__restrict__ images, long long images_cap,
+                                                                   unsigned long long *__restrict__ unit_info, int units_cap,
+                                                                   unsigned int *__restrict__ stage_alloc,  // [frame] words handed out
+                                                                   uint32_t *__restrict__ stage, long long stage_cap_words)
 {
     extern __shared__ __align__(128) unsigned char ent_smem[];
-    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                   // two tile images
+    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                    // two tile images
     uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [2][16] DC code tables
     uint32_t *s_hac = s_hdc + 32;                                                                // [2][256] AC code tables
-    unsigned int *s_bits = reinterpret_cast<unsigned int *>(ent_smem + kEntFdctTiles * kTileImageBytes + kEntTabBytes);  // [0] guard, [1..] bits
-    __shared__ unsigned s_warp[kEntThreads / 32];
-    __shared__ unsigned s_ticket;
-    __shared__ unsigned s_excl_len;
+    unsigned int *s_win_all = s_hac + 512;                                                       // [warp][kWarpWinStride]
+    unsigned int *s_slot_all = s_win_all + kEntWarps * kWarpWinStride;                           // [warp][lane][kSlotStride]
     __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.y, tile = blockIdx.x;
     if (tid == 0) {
-        s_ticket = atomicAdd(ticket, 1u);
         mbar_init(&s_bar, 1);
-    }
-    for (int i = tid; i < kEntPreZeroWords; i += kEntThreads) s_bits[i] = 0;  // while the ticket is on its way
-    __syncthreads();
-    const int f = (int)(s_ticket / (unsigned)tiles_per_frame);
-    const int tile = (int)(s_ticket % (unsigned)tiles_per_frame);
-    if (tid == 0) {
         // images_cap is even, so both images of the tile exist in the buffer even when the second holds no block
         const uint32_t *src = images + ((long long)f * images_cap + (long long)tile * kEntFdctTiles) * kTileImageWords;
         mbar_expect_tx(&s_bar, kEntFdctTiles * kTileImageBytes + kEntTabBytes);
@@ -223,145 +207,222 @@ __global__ void __launch_bounds__(kEntThreads) entropy_kernel(FrameLayout L, Fra
         bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
     }
+    for (int i = tid; i < kEntWarps * kWarpWinStride; i += kEntThreads) s_win_all[i] = 0;  // while the copies are on their way
+    __syncthreads();  // barrier initialised, windows cleared
 
-    const int b = tile * kEntBlocks + tid;
+    // ---- from here on the warp is on its own ----
+    const int u = tile * kEntWarps + warp;                  // unit index inside the frame
+    const int b = u * kUnitBlocks + lane;                   // == tile * kEntBlocks + tid
+    if (u * kUnitBlocks >= L.n_blocks) return;              // trailing unit of the frame's last tile: no block at all
     const bool valid = b < L.n_blocks;
     const int img_i = tid >= kTileBlocks ? 1 : 0, rec_i = tid - img_i * kTileBlocks;
     const uint32_t *rec = s_img + img_i * kTileImageWords + rec_i * kBlkWords;
     const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
     const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
-    mbar_wait(&s_bar, 0); // coefficient images and code tables landed
+    const uint32_t *hdc = s_hdc + 16 * cls, *hac = s_hac + 256 * cls;
+    unsigned int *win = s_win_all + warp * kWarpWinStride;
+    unsigned int *slot = s_slot_all + (warp * kUnitBlocks + lane) * kSlotStride;
+    uint32_t *st = stage + (long long)f * stage_cap_words;
+
+    mbar_wait(&s_bar, 0);  // coefficient images and code tables landed
     unsigned mask_lo = 0, mask_hi = 0;
     if (valid) {
         mask_lo = rec[kMaskLoWord];
         mask_hi = s_img[img_i * kTileImageWords + kMaskHiOff + rec_i];
     }
 
-    // ---- 1. lengths ----
+    // ---- 1. the walk: bits into the private slot, length on the way ----
     unsigned len = 0;
-    if (valid) len = walk_block<false, BitSink>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, nullptr);
+    if (valid) {
+        SlotSink ss;
+        ss.init(slot);
+        walk_block<true, SlotSink>(cb, mask_lo, mask_hi, hdc, hac, &ss);
+        len = ss.bits();
+        ss.flush();
+    }
     unsigned incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned warp_off = 0, tile_len = 0;
-#pragma unroll
-    for (int w = 0; w < kEntThreads / 32; w++) {
-        if (w < warp) warp_off += s_warp[w];
-        tile_len += s_warp[w];
-    }
-    const unsigned off = warp_off + incl - len;
-    const bool windowed = tile_len > (unsigned)kEntWinBits;
+    const unsigned unit_len = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned off = incl - len;
+    const unsigned nwords = (unit_len + 31) >> 5;
 
-    // the length is all a successor's look-back needs: publish it now, and start our own look-back loads
-    unsigned long long *D = descs + (long long)f * tiles_per_frame * 2;  // length words
-    unsigned long long *TW = D + tiles_per_frame;                        // tail words
-    unsigned long long d_look = 0;
-    if (warp == 0) {
-        if (lane == 0) st_desc(&D[tile], desc_pack(tile > 0 ? 1 : 2, tile_len));
-        const int idx = tile - 1 - lane;
-        d_look = idx >= 0 ? ld_desc(&D[idx]) : desc_pack(2, 0);
+    // ---- 3a. reserve the staging words (any order), record the unit ----
+    unsigned pos = 0;
+    if (lane == 0) {
+        pos = atomicAdd(&stage_alloc[f], nwords);
+        unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
+        if ((long long)pos + nwords > stage_cap_words) tabs[f].status = -4;
     }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
 
-    // ---- 2. bits of the tile (or, windowed, only its last 64 bits: enough for the tail word) ----
-    unsigned own_tail;
-    if (!windowed) {
-        const int n_words = (int)((tile_len + 31) >> 5);
-        if (n_words + 2 > kEntPreZeroWords) {  // uniform across the CTA
-            for (int i = kEntPreZeroWords + tid; i <= n_words + 1; i += kEntThreads) s_bits[i] = 0;
-            __syncthreads();
-        }
+    if (unit_len <= (unsigned)kWarpWinBits) {
+        // ---- 2. merge the slots into the warp's window ----
         if (valid) {
-            BitSink sink;
-            sink.init(s_bits + 1, off);
-            walk_block<true, BitSink>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
-            sink.flush();
+            if (len <= (unsigned)kSlotBits) {
+                const int nw = (int)((len + 31) >> 5);
+                for (int i = 0; i < nw; i++) {
+                    const unsigned src = slot[i];
+                    const unsigned dest = off + 32u * i, sh = dest & 31;
+                    unsigned int *w = win + (dest >> 5);
+                    atomicOr(w, src >> sh);
+                    const unsigned spill = sh ? src << (32 - sh) : 0u;
+                    if (spill) atomicOr(w + 1, spill);
+                }
+            } else {
+                BitSink sink;
+                sink.init(win, off);
+                walk_block<true, BitSink>(cb, mask_lo, mask_hi, hdc, hac, &sink);
+                sink.flush();
+            }
         }
-        __syncthreads();
-        own_tail = stream_tail(s_bits, tile_len);
+        __syncwarp();
+        // ---- 3b. stage ----
+        for (unsigned i = lane; i < nwords; i += 32)
+            if ((long long)pos + i < stage_cap_words) st[pos + i] = win[i];
     } else {
-        const unsigned lo = tile_len - 64;
-        if (valid && off + len > lo) {
-            BitSinkClip sink;
-            sink.init(s_bits + 1, off, lo, tile_len);
-            walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
+        for (unsigned lo = 0; lo < unit_len; lo += kWarpWinBits) {
+            const unsigned hi = min(lo + (unsigned)kWarpWinBits, unit_len);
+            __syncwarp();  // previous window fully staged
+            for (int i = lane; i < kWarpWinStride; i += 32) win[i] = 0;
+            __syncwarp();
+            if (valid && off < hi && off + len > lo) {
+                BitSinkClip sink;
+                sink.init(win, off, lo, hi);
+                walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, hdc, hac, &sink);
+            }
+            __syncwarp();
+            const unsigned nw = (hi - lo + 31) >> 5, p0 = pos + (lo >> 5);
+            for (unsigned i = lane; i < nw; i += 32)
+                if ((long long)p0 + i < stage_cap_words) st[p0 + i] = win[i];
         }
-        __syncthreads();
-        own_tail = s_bits[2] & 0x7fffffffu;
     }
+}
 
-    // ---- 3. publish the tail, resolve the exclusive prefix, fetch the tail of the tile in front (warp 0) ----
+// `n` (1..32) bits of a staged unit starting at its bit `start`, right aligned
+__device__ __forceinline__ unsigned staged_bits(const uint32_t *__restrict__ unit_words, unsigned start, unsigned n)
+{
+    const unsigned w = start >> 5, s = start & 31;
+    const unsigned long long two = ((unsigned long long)unit_words[w] << 32) | (s + n > 32 ? unit_words[w + 1] : 0u);
+    return (unsigned)(two >> (64 - s - n)) & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+}
+
+// grid (groups_per_frame * frames), groups taken through a ticket so that every predecessor group is running
+__global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
+                                                                   const unsigned long long *__restrict__ unit_info, int units_cap,
+                                                                   const uint32_t *__restrict__ stage, long long stage_cap_words,
+                                                                   unsigned long long *__restrict__ descs, int groups_per_frame,
+                                                                   unsigned int *__restrict__ ticket, uint32_t *__restrict__ scan,
+                                                                   long long scan_cap_words, unsigned int *__restrict__ chunk_ff, int chunks_cap)
+{
+    __shared__ unsigned long long s_info[kPlaceGroupUnits + 1];   // [0] = the unit in front of the group
+    __shared__ unsigned long long s_excl[kPlaceGroupUnits];       // exclusive bit prefix of each unit inside the frame
+    __shared__ unsigned long long s_wsum[2];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_ticket;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int f = (int)(s_ticket / (unsigned)groups_per_frame);
+    const int g = (int)(s_ticket % (unsigned)groups_per_frame);
+    const int n_units = (L.n_blocks + kUnitBlocks - 1) / kUnitBlocks;
+    const int u0 = g * kPlaceGroupUnits;
+    const int n_here = min(kPlaceGroupUnits, n_units - u0);  // >= 1 by construction of groups_per_frame
+    const unsigned long long *info = unit_info + (long long)f * units_cap;
+
+    // ---- lengths of the group's units, block scan (two warps' worth) ----
+    unsigned long long rec = 0;
+    if (tid < kPlaceGroupUnits && tid < n_here) rec = info[u0 + tid];
+    if (tid < kPlaceGroupUnits) s_info[1 + tid] = rec;
+    if (tid == kPlaceGroupUnits) s_info[0] = u0 > 0 ? info[u0 - 1] : 0ull;
+    unsigned long long incl = unit_bits(rec);
+    if (tid < kPlaceGroupUnits) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+    }
+    __syncthreads();
+    const unsigned long long group_total = s_wsum[0] + s_wsum[1];
+
+    // ---- the group's exclusive prefix: decoupled look-back over the frame's earlier groups (warp 0) ----
+    unsigned long long *D = descs + (long long)f * groups_per_frame;
     if (warp == 0) {
-        if (lane == 0) st_desc(&TW[tile], (1ull << 63) | own_tail);
-        unsigned excl = 0;
-        if (tile > 0) {
-            int basei = tile - 1;
-            unsigned long long d = d_look;
+        if (lane == 0) st_desc(&D[g], desc_pack(g > 0 ? 1 : 2, group_total));
+        unsigned long long excl = 0;
+        if (g > 0) {
+            int basei = g - 1;
             while (true) {
                 const int idx = basei - lane;
+                unsigned long long d;
                 if (idx >= 0) {
-                    while (desc_status(d) == 0) d = ld_desc(&D[idx]);
+                    do { d = ld_desc(&D[idx]); } while (desc_status(d) == 0);
                 } else d = desc_pack(2, 0);
                 const unsigned pm = __ballot_sync(0xffffffffu, desc_status(d) == 2);
                 const int stop = pm ? (__ffs(pm) - 1) : 31;
-                unsigned part = lane <= stop ? desc_len(d) : 0u;
+                unsigned long long part = lane <= stop ? desc_len(d) : 0ull;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                 excl += part;
                 if (pm) break;
                 basei -= 32;
-                const int idx2 = basei - lane;
-                d = idx2 >= 0 ? ld_desc(&D[idx2]) : desc_pack(2, 0);
             }
+            if (lane == 0) st_desc(&D[g], desc_pack(2, excl + group_total));
         }
-        if (lane == 0) {
-            if (tile > 0) st_desc(&D[tile], desc_pack(2, excl + tile_len));
-            s_excl_len = excl;
-            if (tile == tiles_per_frame - 1) state[f].scan_bits = (unsigned long long)excl + tile_len;
-        }
+        if (lane == 0) s_base = excl;
     }
     __syncthreads();
+    if (tid < kPlaceGroupUnits) s_excl[tid] = s_base + (warp ? s_wsum[0] : 0ull) + incl - unit_bits(rec);
+    __syncthreads();
 
-    // ---- 4. shift to the global bit position, store, count 0xFF bytes ----
-    const unsigned P = s_excl_len;
-    // Only the tile's first output word needs bits of the tile in front, and only thread 0 builds that word: it alone
-    // waits for the neighbour's tail, everybody else is already storing.
-    if (tid == 0) {
-        unsigned tail_in = 0;
-        if (tile > 0 && (P & 31)) {
-            unsigned long long t;
-            do { t = ld_desc(&TW[tile - 1]); } while ((t >> 63) == 0);
-            tail_in = (unsigned)t & 0x7fffffffu;
-        }
-        s_bits[0] = tail_in;
-    }
+    // ---- place: one warp per unit, round robin ----
+    const uint32_t *st = stage + (long long)f * stage_cap_words;
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
-    const bool last_tile = tile == tiles_per_frame - 1;
     bool overflow = false;
-    if (!windowed) {
-        overflow = store_run(s_bits, P, tile_len, last_tile, gs, scan_cap_words, cff, tid);
-    } else {
-        __syncthreads();
-        unsigned tail_in = s_bits[0];
-        for (unsigned lo = 0; lo < tile_len; lo += kEntWinBits) {
-            const unsigned hi = min(lo + (unsigned)kEntWinBits, tile_len);
-            __syncthreads();  // previous window fully stored (first round: everybody has read s_bits[0])
-            for (int i = tid; i <= kEntWinWords + 2; i += kEntThreads) s_bits[i] = 0;
-            __syncthreads();
-            if (valid && off < hi && off + len > lo) {
-                BitSinkClip sink;
-                sink.init(s_bits + 1, off, lo, hi);
-                walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, s_hdc + 16 * cls, s_hac + 256 * cls, &sink);
+    for (int i = warp; i < n_here; i += kPlaceThreads / 32) {
+        const unsigned long long r = s_info[1 + i], rp = s_info[i];
+        const unsigned len = unit_bits(r);
+        const unsigned long long P = s_excl[i];
+        const bool final_run = u0 + i == n_units - 1;
+        const unsigned s = (unsigned)(P & 31);
+        const long long W0 = (long long)(P >> 5);
+        const unsigned long long endbit = P + len;
+        long long Wend = (long long)(endbit >> 5);
+        const unsigned used = (unsigned)(endbit & 31);
+        if (final_run && used) Wend++;
+        if (final_run && lane == 0) state[f].scan_bits = endbit;
+        // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
+        const bool staged_ok = (long long)unit_pos(r) + ((len + 31) >> 5) <= stage_cap_words &&
+                               (long long)unit_pos(rp) + ((unit_bits(rp) + 31) >> 5) <= stage_cap_words;
+        if (!staged_ok) { overflow = true; continue; }
+        const uint32_t *uw = st + unit_pos(r), *pw = st + unit_pos(rp);
+        for (long long W = W0 + lane; W < Wend; W += 32) {
+            // global bits [32W, 32W + 32): the first s of word W0 belong to the unit in front, the rest to this one
+            unsigned v;
+            const long long lb = W * 32 - (long long)P;  // local start bit inside this unit (negative only for W0)
+            if (lb < 0) {
+                const unsigned n_own = min(32u - s, len);
+                v = (staged_bits(pw, unit_bits(rp) - s, s) << (32 - s)) | (staged_bits(uw, 0, n_own) << (32 - s - n_own));
+            } else {
+                const unsigned n_own = (unsigned)min((long long)32, (long long)len - lb);
+                v = staged_bits(uw, (unsigned)lb, n_own) << (32 - n_own);
             }
-            if (tid == 0) s_bits[0] = tail_in;
-            __syncthreads();
-            overflow |= store_run(s_bits, P + lo, hi - lo, last_tile && hi == tile_len, gs, scan_cap_words, cff, tid);
-            tail_in = stream_tail(s_bits, hi - lo);  // a full window is longer than 31 bits, so it alone decides the tail
+            if (final_run && used && W == Wend - 1) {
+                const unsigned padn = (8 - (used & 7)) & 7;
+                v |= ((1u << padn) - 1u) << (32 - used - padn);
+            }
+            if (W < scan_cap_words) {
+                gs[W] = __byte_perm(v, 0, 0x0123);
+                const unsigned c = count_ff_bytes(v);
+                if (c) atomicAdd(&cff[W >> kChunkShift], c);
+            } else overflow = true;
         }
     }
     if (overflow) tabs[f].status = -4;

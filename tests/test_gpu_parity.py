@@ -88,7 +88,7 @@ def test_batch_of_different_frames(enc, orc):
 
 
 def test_dense_tiles_take_the_windowed_path(orc):
-    """Noise at qscale 1 needs far more than 64 Kibit per 192-block tile, so K4 runs its windowed emission."""
+    """Noise at qscale 1 needs far more than 8 Kibit per 32-block unit, so K4 runs its windowed emission."""
     import h2j_b200
 
     w, h = 272, 208
@@ -97,7 +97,7 @@ def test_dense_tiles_take_the_windowed_path(orc):
         got = _compare(e, orc, y, u, v, fixed_qscale=1)
         info = e.frame_info(0, 0)
     n_tiles = -(-info.mcu_w * info.mcu_h * 6 // 192)
-    assert info.scan_bits / n_tiles > 65536, "the case no longer exercises the windowed path"
+    assert info.scan_bits / n_tiles > 6 * 8192, "the case no longer exercises the windowed path (8 Kibit per 32-block unit)"
     assert len(got) > 0
 
 
@@ -108,3 +108,27 @@ def test_fixed_qscale_range(orc):
     for q in (1, 3, 31):
         with h2j_b200.Encoder(max_width=160, max_height=96, max_batch=1, n_slots=1, fixed_qscale=q) as e:
             _compare(e, orc, y, u, v, fixed_qscale=q)
+
+
+def test_blocks_larger_than_their_slot_are_emitted_directly(orc):
+    """K4 encodes every block into a private 256-bit slot; a block that needs more is emitted straight into the
+    warp's window instead.  Flat frame with scattered noisy blocks at qscale 1: those blocks need ~600 bits while
+    their 32-block unit stays far below the 8 Kibit window, so both merge paths run side by side in one warp."""
+    import h2j_b200
+
+    w, h = 256, 128
+    rng = np.random.default_rng(77)
+    y = np.full((h, w), 120, np.uint8)
+    u = np.full((h // 2, w // 2), 128, np.uint8)
+    v = np.full((h // 2, w // 2), 128, np.uint8)
+    for (by, bx) in [(0, 0), (1, 5), (3, 7), (8, 30), (15, 31), (9, 9), (9, 10)]:
+        y[by * 8: by * 8 + 8, bx * 8: bx * 8 + 8] = rng.integers(0, 256, (8, 8))
+    u[8:16, 40:48] = rng.integers(0, 256, (8, 8))
+    v[56:64, 120:128] = rng.integers(0, 256, (8, 8))
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, fixed_qscale=1) as e:
+        got = _compare(e, orc, y, u, v, fixed_qscale=1)
+        info = e.frame_info(0, 0)
+    levels, _ = orc.decode_coefs(got)
+    nbits_max = 0
+    assert info.scan_bits < 8192 * (info.mcu_w * info.mcu_h * 6 // 32), "units must stay below the window"
+    assert (np.count_nonzero(levels, axis=1) > 40).sum() >= 7, "expected blocks with far more than 256 bits"
