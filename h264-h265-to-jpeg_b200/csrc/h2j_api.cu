@@ -369,7 +369,8 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     if (!s || !out) return fail(nullptr, H2J_ERR_INVALID_ARG, "null settings/out");
     *out = nullptr;
     if (s->max_width < 2 || s->max_height < 2 || s->max_width > 65500 || s->max_height > 65500 || s->max_batch < 1 || s->n_slots < 1 ||
-        s->n_slots > 8 || s->fixed_qscale < 0 || s->fixed_qscale > 31 || (s->range_mode != 0 && s->range_mode != 1))
+        s->n_slots > 8 || s->fixed_qscale < 0 || s->fixed_qscale > 31 || (s->range_mode != 0 && s->range_mode != 1) ||
+        s->max_jpeg_bytes > ((size_t)256 << 20))  // bit positions inside a frame's scan are 32-bit
         return fail(nullptr, H2J_ERR_INVALID_ARG, "bad settings");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);

@@ -302,15 +302,8 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     }
 }
 
-// `n` (1..32) bits of a staged unit starting at its bit `start`, right aligned
-__device__ __forceinline__ unsigned staged_bits(const uint32_t *__restrict__ unit_words, unsigned start, unsigned n)
-{
-    const unsigned w = start >> 5, s = start & 31;
-    const unsigned long long two = ((unsigned long long)unit_words[w] << 32) | (s + n > 32 ? unit_words[w + 1] : 0u);
-    return (unsigned)(two >> (64 - s - n)) & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
-}
-
-// grid (groups_per_frame * frames), groups taken through a ticket so that every predecessor group is running
+// grid (groups_per_frame * frames), groups taken through a ticket so that every predecessor group is running.
+// Bit positions are 32-bit: h2j_create bounds max_jpeg_bytes to 256 MiB.
 __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
                                                                    const unsigned long long *__restrict__ unit_info, int units_cap,
                                                                    const uint32_t *__restrict__ stage, long long stage_cap_words,
@@ -318,10 +311,11 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
                                                                    unsigned int *__restrict__ ticket, uint32_t *__restrict__ scan,
                                                                    long long scan_cap_words, unsigned int *__restrict__ chunk_ff, int chunks_cap)
 {
-    __shared__ unsigned long long s_info[kPlaceGroupUnits + 1];   // [0] = the unit in front of the group
-    __shared__ unsigned long long s_excl[kPlaceGroupUnits];       // exclusive bit prefix of each unit inside the frame
-    __shared__ unsigned long long s_wsum[2];
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_pos[kPlaceGroupUnits + 1];    // staging position of the unit; [0] = the unit in front of the group
+    __shared__ unsigned s_len[kPlaceGroupUnits + 1];    // its bit length
+    __shared__ unsigned s_excl[kPlaceGroupUnits + 1];   // exclusive bit prefix inside the frame; [n_here] = end of the group
+    __shared__ unsigned s_wsum[2];
+    __shared__ unsigned s_base;
     __shared__ unsigned s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,26 +330,27 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
 
     // ---- lengths of the group's units, block scan (two warps' worth) ----
     unsigned long long rec = 0;
-    if (tid < kPlaceGroupUnits && tid < n_here) rec = info[u0 + tid];
-    if (tid < kPlaceGroupUnits) s_info[1 + tid] = rec;
-    if (tid == kPlaceGroupUnits) s_info[0] = u0 > 0 ? info[u0 - 1] : 0ull;
-    unsigned long long incl = unit_bits(rec);
+    if (tid < n_here) rec = info[u0 + tid];
+    else if (tid == kPlaceGroupUnits && u0 > 0) rec = info[u0 - 1];
+    if (tid < kPlaceGroupUnits) { s_pos[1 + tid] = unit_pos(rec); s_len[1 + tid] = unit_bits(rec); }
+    if (tid == kPlaceGroupUnits) { s_pos[0] = unit_pos(rec); s_len[0] = unit_bits(rec); }
+    unsigned incl = tid < kPlaceGroupUnits ? unit_bits(rec) : 0u;
     if (tid < kPlaceGroupUnits) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
         if (lane == 31) s_wsum[warp] = incl;
     }
     __syncthreads();
-    const unsigned long long group_total = s_wsum[0] + s_wsum[1];
+    const unsigned group_total = s_wsum[0] + s_wsum[1];
 
     // ---- the group's exclusive prefix: decoupled look-back over the frame's earlier groups (warp 0) ----
     unsigned long long *D = descs + (long long)f * groups_per_frame;
     if (warp == 0) {
         if (lane == 0) st_desc(&D[g], desc_pack(g > 0 ? 1 : 2, group_total));
-        unsigned long long excl = 0;
+        unsigned excl = 0;
         if (g > 0) {
             int basei = g - 1;
             while (true) {
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
                 } else d = desc_pack(2, 0);
                 const unsigned pm = __ballot_sync(0xffffffffu, desc_status(d) == 2);
                 const int stop = pm ? (__ffs(pm) - 1) : 31;
-                unsigned long long part = lane <= stop ? desc_len(d) : 0ull;
+                unsigned part = lane <= stop ? (unsigned)desc_len(d) : 0u;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                 excl += part;
@@ -375,55 +370,69 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             }
             if (lane == 0) st_desc(&D[g], desc_pack(2, excl + group_total));
         }
-        if (lane == 0) s_base = excl;
+        if (lane == 0) { s_base = excl; s_excl[n_here] = excl + group_total; }
     }
     __syncthreads();
-    if (tid < kPlaceGroupUnits) s_excl[tid] = s_base + (warp ? s_wsum[0] : 0ull) + incl - unit_bits(rec);
+    if (tid < n_here) s_excl[tid] = s_base + (warp ? s_wsum[0] : 0u) + incl - unit_bits(rec);
     __syncthreads();
 
-    // ---- place: one warp per unit, round robin ----
+    // ---- place: the group's output words as one flat range, a word per thread and step; the owning unit (the one
+    //      that holds the word's last bit) is found by bisection over the prefix table ----
     const uint32_t *st = stage + (long long)f * stage_cap_words;
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
+    const bool has_final = u0 + n_here == n_units;
+    const unsigned P0 = s_excl[0], Pend = s_excl[n_here];
+    const unsigned Wbeg = P0 >> 5;
+    unsigned Wstop = Pend >> 5;
+    const unsigned used_end = Pend & 31;
+    if (has_final && used_end) Wstop++;
+    if (has_final && tid == 0) state[f].scan_bits = Pend;
     bool overflow = false;
-    for (int i = warp; i < n_here; i += kPlaceThreads / 32) {
-        const unsigned long long r = s_info[1 + i], rp = s_info[i];
-        const unsigned len = unit_bits(r);
-        const unsigned long long P = s_excl[i];
-        const bool final_run = u0 + i == n_units - 1;
-        const unsigned s = (unsigned)(P & 31);
-        const long long W0 = (long long)(P >> 5);
-        const unsigned long long endbit = P + len;
-        long long Wend = (long long)(endbit >> 5);
-        const unsigned used = (unsigned)(endbit & 31);
-        if (final_run && used) Wend++;
-        if (final_run && lane == 0) state[f].scan_bits = endbit;
-        // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
-        const bool staged_ok = (long long)unit_pos(r) + ((len + 31) >> 5) <= stage_cap_words &&
-                               (long long)unit_pos(rp) + ((unit_bits(rp) + 31) >> 5) <= stage_cap_words;
-        if (!staged_ok) { overflow = true; continue; }
-        const uint32_t *uw = st + unit_pos(r), *pw = st + unit_pos(rp);
-        for (long long W = W0 + lane; W < Wend; W += 32) {
-            // global bits [32W, 32W + 32): the first s of word W0 belong to the unit in front, the rest to this one
-            unsigned v;
-            const long long lb = W * 32 - (long long)P;  // local start bit inside this unit (negative only for W0)
-            if (lb < 0) {
-                const unsigned n_own = min(32u - s, len);
-                v = (staged_bits(pw, unit_bits(rp) - s, s) << (32 - s)) | (staged_bits(uw, 0, n_own) << (32 - s - n_own));
-            } else {
-                const unsigned n_own = (unsigned)min((long long)32, (long long)len - lb);
-                v = staged_bits(uw, (unsigned)lb, n_own) << (32 - n_own);
-            }
-            if (final_run && used && W == Wend - 1) {
-                const unsigned padn = (8 - (used & 7)) & 7;
-                v |= ((1u << padn) - 1u) << (32 - used - padn);
-            }
-            if (W < scan_cap_words) {
-                gs[W] = __byte_perm(v, 0, 0x0123);
-                const unsigned c = count_ff_bytes(v);
-                if (c) atomicAdd(&cff[W >> kChunkShift], c);
-            } else overflow = true;
+    for (unsigned W = Wbeg + tid; W < Wstop; W += kPlaceThreads) {
+        const unsigned lastbit = min(W * 32 + 31, Pend - 1);  // (the frame's final partial word: the stream's last bit)
+        int lo = 0, hi = n_here - 1;  // largest i with s_excl[i] <= lastbit
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_excl[mid] <= lastbit) lo = mid;
+            else hi = mid - 1;
         }
+        const unsigned len = s_len[1 + lo], pos = s_pos[1 + lo], P = s_excl[lo];
+        const unsigned plen = s_len[lo], ppos = s_pos[lo];
+        // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
+        if ((long long)pos + ((len + 31) >> 5) > stage_cap_words || (long long)ppos + ((plen + 31) >> 5) > stage_cap_words) {
+            overflow = true;
+            continue;
+        }
+        const uint32_t *uw = st + pos;
+        // global bits [32W, 32W + 32).  Bits in front of P belong to the unit in front (a unit is never shorter than a
+        // word unless it is the frame's last, so at most two units meet in one word); the word's last bit is ours, so
+        // everything from our first bit in the word up to its end is inside this unit -- except in the frame's last word.
+        unsigned v;
+        if (W * 32 < P) {
+            const unsigned s = P - W * 32;  // 1..31 bits of the neighbour: its last s bits
+            const uint32_t *pw = st + ppos;
+            const unsigned lw = (plen - 1) >> 5, q = ((plen - 1) & 31) + 1;  // its last word and the bits used in it
+            const unsigned hiw = lw ? pw[lw - 1] : 0u;
+            const unsigned tail = __funnelshift_r(pw[lw], hiw, 32 - q);  // the neighbour's last 32 bits, right aligned
+            v = (tail << (32 - s)) | (uw[0] >> s);
+        } else {
+            const unsigned lb = W * 32 - P, w = lb >> 5, sh = lb & 31;
+            // sh != 0: bit lb + 31 lies in word w + 1, which is ours unless this is the frame's last, partial word
+            const unsigned a = uw[w], b2 = (sh && w + 1 < ((len + 31) >> 5)) ? uw[w + 1] : 0u;
+            v = __funnelshift_l(b2, a, sh);
+        }
+        if (has_final && W == Wstop - 1 && used_end) {
+            // staged units are zero behind their last bit; bits of the word that lie behind the stream get the 1-padding
+            const unsigned padn = (8 - (used_end & 7)) & 7;
+            v &= ~(0xffffffffu >> used_end);
+            v |= ((1u << padn) - 1u) << (32 - used_end - padn);
+        }
+        if (W < scan_cap_words) {
+            gs[W] = __byte_perm(v, 0, 0x0123);
+            const unsigned c = count_ff_bytes(v);
+            if (c) atomicAdd(&cff[W >> kChunkShift], c);
+        } else overflow = true;
     }
     if (overflow) tabs[f].status = -4;
 }

@@ -59,7 +59,7 @@ typedef struct h2j_settings {
     int range_mode;        /* h2j_range_mode */
     int fixed_qscale;      /* 0: the reference's first-frame rate control decides (default);
                               1..31: force it (AV_CODEC_FLAG_QSCALE equivalent; not used by the reference) */
-    size_t max_jpeg_bytes; /* per-frame output capacity; 0 = 2 MiB, the reference's HEAP_SIZE */
+    size_t max_jpeg_bytes; /* per-frame output capacity; 0 = 2 MiB, the reference's HEAP_SIZE; at most 256 MiB */
     const char *comment;   /* COM segment payload; NULL = "Lavc58.117.101", the LIBAVCODEC_IDENT of the
                               ffmpeg build the reference links on x86-64 (lib/ffmpeg/x86_64_shared) */
     int profile;           /* non-zero: bracket every kernel with CUDA events (see h2j_slot_kernel_ms) */
