@@ -408,8 +408,15 @@ def run_ours(a):
         per_kernel[name] = entry
     dom = max((k for k in per_kernel if k in ("fdct_quant_kernel", "entropy_walk_kernel", "mbvar_kernel", "stuff_kernel", "scan_place_kernel")),
               key=lambda k: per_kernel[k]["avg_ms"])
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per frame of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["kernels"][dom]["dram_bytes_per_frame"] * SB
+        traffic_src = f"{tj['source']} ({tj['frames_per_launch']}-frame launch, scaled to {SB})"
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": per_kernel[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": per_kernel[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes[dom] * SB,
             "note": "per-kernel CUDA events on the launching stream inside the timed region (one slot: no other stream's kernels "
                     "inside a bracket)" if NS == 1 else "per-kernel CUDA events on the launching stream; several slots in flight, so a "
