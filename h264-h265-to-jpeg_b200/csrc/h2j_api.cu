@@ -22,7 +22,7 @@ thread_local std::string g_create_error;
 
 struct KernelTiming {
     const char *name;
-    cudaEvent_t start, stop;
+    int start, stop;  // indices into Slot::events; back-to-back kernels share the event between them
 };
 
 struct Slot {
@@ -56,7 +56,9 @@ struct Slot {
     int n = 0;
     FrameLayout L{};
     std::vector<KernelTiming> timings;
-    int timings_used = 0;
+    std::vector<cudaEvent_t> events;
+    int timings_used = 0, events_used = 0;
+    bool chain = false;  // the last thing enqueued was a timed kernel: its stop event is the next kernel's start
 };
 
 }  // namespace
@@ -186,20 +188,30 @@ struct ScopedTiming {
     Slot &sl;
     bool on;
     int idx = -1;
+    static int record(Slot &sl)
+    {
+        if (sl.events_used == (int)sl.events.size()) {
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            sl.events.push_back(ev);
+        }
+        cudaEventRecord(sl.events[sl.events_used], sl.stream);
+        return sl.events_used++;
+    }
     ScopedTiming(h2j_encoder *e, Slot &s, const char *name) : sl(s), on(e->s.profile != 0)
     {
         if (!on) return;
-        if (sl.timings_used == (int)sl.timings.size()) {
-            KernelTiming t{name, nullptr, nullptr};
-            cudaEventCreate(&t.start);
-            cudaEventCreate(&t.stop);
-            sl.timings.push_back(t);
-        }
+        if (sl.timings_used == (int)sl.timings.size()) sl.timings.push_back(KernelTiming{name, -1, -1});
         idx = sl.timings_used++;
         sl.timings[idx].name = name;
-        cudaEventRecord(sl.timings[idx].start, sl.stream);
+        sl.timings[idx].start = (sl.chain && sl.events_used > 0) ? sl.events_used - 1 : record(sl);
     }
-    ~ScopedTiming() { if (on) cudaEventRecord(sl.timings[idx].stop, sl.stream); }
+    ~ScopedTiming()
+    {
+        if (!on) return;
+        sl.timings[idx].stop = record(sl);
+        sl.chain = true;
+    }
 };
 
 // Enqueue the whole pipeline for `n` frames at `d_frames` on the slot's stream.
@@ -210,6 +222,8 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     const FrameLayout &L = sl.L;
     cudaStream_t st = sl.stream;
     sl.timings_used = 0;
+    sl.events_used = 0;
+    sl.chain = false;
     CU(e, cudaMemsetAsync(sl.d_zero, 0, sl.zero_bytes, st));
     {
         ScopedTiming t(e, sl, "mbvar_kernel");
@@ -276,6 +290,7 @@ int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
         pack_kernel<<<dim3(8, sl.n), 256, 0, st>>>(sl.d_out, (long long)e->out_cap, sl.d_offsets, sl.d_packed);
         e->launches++;
     }
+    sl.chain = false;
     CU(e, cudaMemcpyAsync(sl.h_offsets, sl.d_offsets, sizeof(unsigned long long) * (sl.n + 1), cudaMemcpyDeviceToHost, st));
     CU(e, cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(int) * sl.n, cudaMemcpyDeviceToHost, st));
     CU(e, cudaEventRecord(sl.ev_done, st));
@@ -299,7 +314,7 @@ void free_slot(Slot &sl)
     if (sl.h_status) cudaFreeHost(sl.h_status);
     if (sl.h_sizes) cudaFreeHost(sl.h_sizes);
     if (sl.h_stage) cudaFreeHost(sl.h_stage);
-    for (auto &t : sl.timings) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+    for (auto &ev : sl.events) cudaEventDestroy(ev);
     if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     if (sl.stream && sl.own_stream) cudaStreamDestroy(sl.stream);
@@ -723,7 +738,7 @@ int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, 
     int n = 0;
     for (int i = 0; i < sl.timings_used && n < cap; i++, n++) {
         float t = 0.f;
-        CU(e, cudaEventElapsedTime(&t, sl.timings[i].start, sl.timings[i].stop));
+        CU(e, cudaEventElapsedTime(&t, sl.events[sl.timings[i].start], sl.events[sl.timings[i].stop]));
         if (names) names[n] = sl.timings[i].name;
         if (ms) ms[n] = t;
     }

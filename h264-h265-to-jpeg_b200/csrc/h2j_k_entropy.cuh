@@ -50,7 +50,7 @@ constexpr int kWarpWinStride = kWarpWinWords + 4;            // spare words for 
 constexpr int kSlotWords = 8;                                // private slot of a block: 256 bits
 constexpr int kSlotBits = kSlotWords * 32;
 constexpr int kSlotStride = kSlotWords + 1;                  // odd stride: the lanes' word i never share a bank
-constexpr int kPlaceGroupUnits = 64;                         // K4b: units per CTA
+constexpr int kPlaceGroupUnits = 256;                        // K4b: units per CTA, one per thread
 constexpr int kPlaceThreads = 256;
 
 // per-unit record written by K4a: where the unit's bits were staged and how many there are
@@ -311,10 +311,11 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
                                                                    unsigned int *__restrict__ ticket, uint32_t *__restrict__ scan,
                                                                    long long scan_cap_words, unsigned int *__restrict__ chunk_ff, int chunks_cap)
 {
+    static_assert(kPlaceGroupUnits == kPlaceThreads, "one unit per thread in the scan");
     __shared__ unsigned s_pos[kPlaceGroupUnits + 1];    // staging position of the unit; [0] = the unit in front of the group
     __shared__ unsigned s_len[kPlaceGroupUnits + 1];    // its bit length
     __shared__ unsigned s_excl[kPlaceGroupUnits + 1];   // exclusive bit prefix inside the frame; [n_here] = end of the group
-    __shared__ unsigned s_wsum[2];
+    __shared__ unsigned s_wsum[kPlaceThreads / 32];
     __shared__ unsigned s_base;
     __shared__ unsigned s_ticket;
 
@@ -328,23 +329,29 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     const int n_here = min(kPlaceGroupUnits, n_units - u0);  // >= 1 by construction of groups_per_frame
     const unsigned long long *info = unit_info + (long long)f * units_cap;
 
-    // ---- lengths of the group's units, block scan (two warps' worth) ----
-    unsigned long long rec = 0;
-    if (tid < n_here) rec = info[u0 + tid];
-    else if (tid == kPlaceGroupUnits && u0 > 0) rec = info[u0 - 1];
-    if (tid < kPlaceGroupUnits) { s_pos[1 + tid] = unit_pos(rec); s_len[1 + tid] = unit_bits(rec); }
-    if (tid == kPlaceGroupUnits) { s_pos[0] = unit_pos(rec); s_len[0] = unit_bits(rec); }
-    unsigned incl = tid < kPlaceGroupUnits ? unit_bits(rec) : 0u;
-    if (tid < kPlaceGroupUnits) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
+    // ---- lengths of the group's units, block scan ----
+    const unsigned long long rec = tid < n_here ? info[u0 + tid] : 0ull;
+    s_pos[1 + tid] = unit_pos(rec);
+    s_len[1 + tid] = unit_bits(rec);
+    if (tid == 0) {
+        const unsigned long long rp = u0 > 0 ? info[u0 - 1] : 0ull;
+        s_pos[0] = unit_pos(rp);
+        s_len[0] = unit_bits(rp);
     }
+    unsigned incl = unit_bits(rec);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    const unsigned group_total = s_wsum[0] + s_wsum[1];
+    unsigned warp_off = 0, group_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPlaceThreads / 32; w++) {
+        if (w < warp) warp_off += s_wsum[w];
+        group_total += s_wsum[w];
+    }
 
     // ---- the group's exclusive prefix: decoupled look-back over the frame's earlier groups (warp 0) ----
     unsigned long long *D = descs + (long long)f * groups_per_frame;
@@ -373,11 +380,12 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
         if (lane == 0) { s_base = excl; s_excl[n_here] = excl + group_total; }
     }
     __syncthreads();
-    if (tid < n_here) s_excl[tid] = s_base + (warp ? s_wsum[0] : 0u) + incl - unit_bits(rec);
+    if (tid < n_here) s_excl[tid] = s_base + warp_off + incl - unit_bits(rec);
     __syncthreads();
 
-    // ---- place: the group's output words as one flat range, a word per thread and step; the owning unit (the one
-    //      that holds the word's last bit) is found by bisection over the prefix table ----
+    // ---- place: the group's output words as one flat range, four consecutive words (one 16-byte store) per thread and
+    //      step.  The unit that owns a word (the one holding its last bit) is found by bisection over the prefix table for
+    //      the first of the four and by stepping forward for the rest. ----
     const uint32_t *st = stage + (long long)f * stage_cap_words;
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
@@ -389,50 +397,79 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     if (has_final && used_end) Wstop++;
     if (has_final && tid == 0) state[f].scan_bits = Pend;
     bool overflow = false;
-    for (unsigned W = Wbeg + tid; W < Wstop; W += kPlaceThreads) {
-        const unsigned lastbit = min(W * 32 + 31, Pend - 1);  // (the frame's final partial word: the stream's last bit)
-        int lo = 0, hi = n_here - 1;  // largest i with s_excl[i] <= lastbit
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_excl[mid] <= lastbit) lo = mid;
-            else hi = mid - 1;
+    for (unsigned Q = (Wbeg >> 2) + tid; Q * 4 < Wstop; Q += kPlaceThreads) {
+        unsigned v[4] = {0, 0, 0, 0};
+        bool have[4];
+        int i = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned W = Q * 4 + k;
+            have[k] = W >= Wbeg && W < Wstop;
+            if (!have[k]) continue;
+            const unsigned lastbit = min(W * 32 + 31, Pend - 1);  // (the frame's final partial word: the stream's last bit)
+            if (i < 0) {
+                int lo = 0, hi = n_here - 1;  // largest i with s_excl[i] <= lastbit
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_excl[mid] <= lastbit) lo = mid;
+                    else hi = mid - 1;
+                }
+                i = lo;
+            } else {
+                while (s_excl[i + 1] <= lastbit) i++;  // s_excl[n_here] = Pend > lastbit bounds the walk
+            }
+            const unsigned len = s_len[1 + i], pos = s_pos[1 + i], P = s_excl[i];
+            const unsigned plen = s_len[i], ppos = s_pos[i];
+            // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
+            if ((long long)pos + ((len + 31) >> 5) > stage_cap_words || (long long)ppos + ((plen + 31) >> 5) > stage_cap_words) {
+                overflow = true;
+                have[k] = false;
+                continue;
+            }
+            const uint32_t *uw = st + pos;
+            // global bits [32W, 32W + 32).  Bits in front of P belong to the unit in front (a unit is never shorter than a
+            // word unless it is the frame's last, so at most two units meet in one word); the word's last bit is ours, so
+            // everything from our first bit in the word up to its end is inside this unit -- except in the frame's last word.
+            unsigned x;
+            if (W * 32 < P) {
+                const unsigned s = P - W * 32;  // 1..31 bits of the neighbour: its last s bits
+                const uint32_t *pw = st + ppos;
+                const unsigned lw = (plen - 1) >> 5, q = ((plen - 1) & 31) + 1;  // its last word and the bits used in it
+                const unsigned hiw = lw ? __ldg(pw + lw - 1) : 0u;
+                const unsigned tail = __funnelshift_r(__ldg(pw + lw), hiw, 32 - q);  // the neighbour's last 32 bits, right aligned
+                x = (tail << (32 - s)) | (__ldg(uw) >> s);
+            } else {
+                const unsigned lb = W * 32 - P, w = lb >> 5, sh = lb & 31;
+                // sh != 0: bit lb + 31 lies in word w + 1, which is ours unless this is the frame's last, partial word
+                const unsigned a = __ldg(uw + w), b2 = (sh && w + 1 < ((len + 31) >> 5)) ? __ldg(uw + w + 1) : 0u;
+                x = __funnelshift_l(b2, a, sh);
+            }
+            if (has_final && W == Wstop - 1 && used_end) {
+                // bits of the word that lie behind the stream get the 1-padding up to the byte boundary, zeros after it
+                const unsigned padn = (8 - (used_end & 7)) & 7;
+                x &= ~(0xffffffffu >> used_end);
+                x |= ((1u << padn) - 1u) << (32 - used_end - padn);
+            }
+            v[k] = x;
         }
-        const unsigned len = s_len[1 + lo], pos = s_pos[1 + lo], P = s_excl[lo];
-        const unsigned plen = s_len[lo], ppos = s_pos[lo];
-        // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
-        if ((long long)pos + ((len + 31) >> 5) > stage_cap_words || (long long)ppos + ((plen + 31) >> 5) > stage_cap_words) {
-            overflow = true;
-            continue;
+        unsigned c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (have[k]) c += count_ff_bytes(v[k]);
+            v[k] = __byte_perm(v[k], 0, 0x0123);
         }
-        const uint32_t *uw = st + pos;
-        // global bits [32W, 32W + 32).  Bits in front of P belong to the unit in front (a unit is never shorter than a
-        // word unless it is the frame's last, so at most two units meet in one word); the word's last bit is ours, so
-        // everything from our first bit in the word up to its end is inside this unit -- except in the frame's last word.
-        unsigned v;
-        if (W * 32 < P) {
-            const unsigned s = P - W * 32;  // 1..31 bits of the neighbour: its last s bits
-            const uint32_t *pw = st + ppos;
-            const unsigned lw = (plen - 1) >> 5, q = ((plen - 1) & 31) + 1;  // its last word and the bits used in it
-            const unsigned hiw = lw ? pw[lw - 1] : 0u;
-            const unsigned tail = __funnelshift_r(pw[lw], hiw, 32 - q);  // the neighbour's last 32 bits, right aligned
-            v = (tail << (32 - s)) | (uw[0] >> s);
+        const unsigned W0 = Q * 4;
+        if (have[0] && have[1] && have[2] && have[3] && (long long)W0 + 4 <= scan_cap_words) {
+            *reinterpret_cast<uint4 *>(gs + W0) = make_uint4(v[0], v[1], v[2], v[3]);
         } else {
-            const unsigned lb = W * 32 - P, w = lb >> 5, sh = lb & 31;
-            // sh != 0: bit lb + 31 lies in word w + 1, which is ours unless this is the frame's last, partial word
-            const unsigned a = uw[w], b2 = (sh && w + 1 < ((len + 31) >> 5)) ? uw[w + 1] : 0u;
-            v = __funnelshift_l(b2, a, sh);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!have[k]) continue;
+                if ((long long)W0 + k < scan_cap_words) gs[W0 + k] = v[k];
+                else overflow = true;
+            }
         }
-        if (has_final && W == Wstop - 1 && used_end) {
-            // staged units are zero behind their last bit; bits of the word that lie behind the stream get the 1-padding
-            const unsigned padn = (8 - (used_end & 7)) & 7;
-            v &= ~(0xffffffffu >> used_end);
-            v |= ((1u << padn) - 1u) << (32 - used_end - padn);
-        }
-        if (W < scan_cap_words) {
-            gs[W] = __byte_perm(v, 0, 0x0123);
-            const unsigned c = count_ff_bytes(v);
-            if (c) atomicAdd(&cff[W >> kChunkShift], c);
-        } else overflow = true;
+        if (c) atomicAdd(&cff[W0 >> kChunkShift], c);  // the four words share a chunk
     }
     if (overflow) tabs[f].status = -4;
 }
