@@ -286,21 +286,43 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             rec[0] = (uint32_t)(diff & 0xffff) | word0_hi;
             atomicAdd(&s_dchist[cls][mag_bits(diff)], 1u);
             // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
+            // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
+            // below it and its value, so the levels can be visited in any order.  Positions 1..31 (where nearly all of
+            // them are) are taken from both ends at once: two independent bit-scan -> load -> size -> atomic chains per
+            // iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
             unsigned int *hist = s_hist[cls];
-            int prev = 0;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                unsigned mm = half ? mask_hi : mask_lo;
-                while (mm) {
-                    const int bp = __ffs((int)mm) - 1, k = half * 32 + bp;
-                    mm &= mm - 1;
-                    const int run = k - prev - 1;
-                    prev = k;
-                    const int nb = mag_bits((int)lv[2 * bp + half]);
-                    if (run >= 16) atomicAdd(&hist[0xf0], (unsigned)(run >> 4));
-                    atomicAdd(&hist[((run & 15) << 4) | nb], 1u);
+            auto count = [&](int k, int below, int val) {
+                const int run = k - below - 1, nb = mag_bits(val);
+                if (run >= 16) atomicAdd(&hist[0xf0], (unsigned)(run >> 4));
+                atomicAdd(&hist[((run & 15) << 4) | nb], 1u);
+            };
+            unsigned lo = mask_lo;
+            const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
+            int below_a = 0;   // ascending end: the non-zero position below the next one taken
+            int kb = top_lo;   // descending end: the highest position still in `lo`
+            while (lo) {
+                const unsigned bit_a = lo & (0u - lo);
+                const int ka = 31 - __clz(bit_a);
+                lo ^= bit_a;
+                const int val_a = (int)lv[2 * ka];
+                if (lo) {  // ka was not the last one: kb is a different position
+                    lo ^= 1u << kb;
+                    const int val_b = (int)lv[2 * kb];
+                    const int below_b = lo ? 31 - __clz(lo) : ka;  // next one down, or the one the other end just took
+                    count(kb, below_b, val_b);
+                    kb = below_b;
                 }
+                count(ka, below_a, val_a);
+                below_a = ka;
+            }
+            int prev = top_lo;
+            unsigned hi = mask_hi;
+            while (hi) {
+                const int bp = __ffs((int)hi) - 1, k = 32 + bp;
+                hi &= hi - 1;
+                count(k, prev, (int)lv[2 * bp + 1]);
+                prev = k;
             }
             if (prev < 63) atomicAdd(&hist[0], 1u);
         }
