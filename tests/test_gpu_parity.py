@@ -132,3 +132,19 @@ def test_blocks_larger_than_their_slot_are_emitted_directly(orc):
     nbits_max = 0
     assert info.scan_bits < 8192 * (info.mcu_w * info.mcu_h * 6 // 32), "units must stay below the window"
     assert (np.count_nonzero(levels, axis=1) > 40).sum() >= 7, "expected blocks with far more than 256 bits"
+
+
+@pytest.mark.parametrize("w,h", [(65500, 16), (16, 65500), (4096, 18), (7680, 4320), (2, 4098)])
+def test_extreme_geometries(orc, w, h):
+    """The JPEG limit (65500), thin strips in both directions (tiles wrap an MCU row every MCU / never), and an 8K frame
+    (129,600 MCUs: grid, prefix and staging arithmetic well past the 1080p sizes)."""
+    import h2j_b200
+
+    y, u, v = orc.synth_planes(w, h, "textured", seed=w + h, amp=45)
+    cap = max(2 * 1024 * 1024, w * h)
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, max_jpeg_bytes=cap) as e:
+        got = e.yuv2jpeg(y, u, v)
+        info = e.frame_info(0, 0)
+    want, dbg, _ = orc.oracle_encode(y, u, v)
+    assert info.qscale == dbg.qscale and info.scan_bits == dbg.scan_bits
+    assert got == want
