@@ -2,14 +2,15 @@
 // mjpeg encoder as the reference configures it) as sm_100a kernels.  One launch handles a batch of same-sized
 // frames; frames never interact, so the batch index is simply a grid dimension.
 //
-//   K1  mbvar_kernel        luma 16x16 variance sums -> rate-control input              (HBM bound, 1 B/px read)
-//   K2  fdct_quant_kernel   qscale + quantiser set-up, (range convert +) edge replicate + FDCT + quantise +
-//                           zigzag + DC prediction + DC/AC symbol histograms           (issue bound)
-//   K3  huffman_kernel      4 optimal (package-merge) tables, code tables, JPEG header
-//   K4  entropy_kernel      per-block bit lengths, decoupled look-back scan over tiles, bit packing, 0xFF census
-//   K5  stuff_kernel        0xFF -> 0xFF00 expansion behind the header, EOI, final size
-//   K6  pack_kernel         optional: JPEGs of a batch packed back to back for one D2H copy
-//   convert_pad_kernel      kernel 1 on its own: range convert + MCU padding to planes (h2j_convert_pad)
+//   K1  mbvar_kernel         luma 16x16 variance sums -> rate-control input              (HBM bound, 1 B/px read)
+//   K2  fdct_quant_kernel    qscale + quantiser set-up, (range convert +) edge replicate + FDCT + quantise +
+//                            zigzag + DC prediction + DC/AC symbol histograms           (integer issue bound)
+//   K3  huffman_kernel       4 optimal (package-merge) tables, code tables, JPEG header
+//   K4a entropy_walk_kernel  one walk per block into private slots, warp scan, merge, staging of 32-block units
+//   K4b scan_place_kernel    unit lengths scanned (decoupled look-back over groups), units shifted into the scan, 0xFF census
+//   K5  stuff_kernel         0xFF -> 0xFF00 expansion behind the header, EOI, final size
+//   K6  pack_kernel          optional: JPEGs of a batch packed back to back for one D2H copy
+//   convert_pad_kernel       kernel 1 on its own: range convert + MCU padding to planes (h2j_convert_pad)
 //
 // This header: the layout shared by host and device, constants and small helpers.
 #pragma once

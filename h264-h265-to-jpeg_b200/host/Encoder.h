@@ -60,4 +60,13 @@ private:
 // limited-range input to full range first (the reference does not).  Call before the first yuv2Jpeg.
 extern "C" void h2j_host_configure(int cuda_device, int range_mode);
 
+// Batch scope for services that convert many pictures (the reference has no such call: a loop over
+// IDecoder::H265ToJpeg is what it offers).  Between begin and end, yuv2Jpeg() -- and therefore the unchanged
+// IDecoder::H265ToJpeg() that calls it (reference src/Decoder.cpp:319) -- only copies the decoded planes into pinned
+// staging and returns true; the GPU encodes the queued pictures `max_frames` at a time (runs of equal size as one
+// batch) and the JPEG files are written then.  h2j_host_batch_end() drains the queue and returns the number of files
+// written (-1 outside a scope); *failed receives the number of pictures that could not be encoded or saved.
+extern "C" int h2j_host_batch_begin(int max_frames);
+extern "C" int h2j_host_batch_end(int *failed);
+
 #endif  // H2J_HOST_ENCODER_H

@@ -56,3 +56,55 @@ def test_dropin_library_on_the_reference_fixtures(orc, name, tmp_path):
         ref_out = str(tmp_path / (name + ".ref.jpeg"))
         assert orc.reference().ref_h265_to_jpeg(src.encode(), ref_out.encode(), 1) == 1
         assert got == open(ref_out, "rb").read()
+
+
+def test_host_batch_scope_mixed_sizes(orc, tmp_path):
+    """h2j_host_batch_begin/end: yuv2Jpeg only queues, the GPU encodes runs of equal-sized pictures as batches, the files
+    appear at the latest when the scope ends, and every file is byte-identical to the oracle."""
+    lib = C.CDLL(HOST_SO)
+    lib.h2j_host_yuv2jpeg_file.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    lib.h2j_host_batch_end.argtypes = [C.POINTER(C.c_int)]
+    assert lib.h2j_host_batch_end(None) == -1  # no scope open
+    assert lib.h2j_host_batch_begin(4) == 0
+    assert lib.h2j_host_batch_begin(4) == -1   # already open
+    sizes = [(322, 242), (322, 242), (322, 242), (64, 64), (64, 64), (640, 368), (322, 242)]  # a bigger one forces a pool re-cut
+    want, outs = [], []
+    for i, (w, h) in enumerate(sizes):
+        y, u, v = orc.synth_planes(w, h, "textured", seed=50 + i, amp=25 + 5 * i)
+        out = str(tmp_path / f"b_{i}.jpeg")
+        assert lib.h2j_host_yuv2jpeg_file(y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], w, h, 0,
+                                          out.encode()) == 1
+        want.append(orc.oracle_encode(y, u, v)[0])
+        outs.append(out)
+    assert not os.path.exists(outs[-1])  # the tail of the queue is still waiting
+    failed = C.c_int(-1)
+    assert lib.h2j_host_batch_end(C.byref(failed)) == len(sizes) and failed.value == 0
+    for out, w_ in zip(outs, want):
+        assert open(out, "rb").read() == w_
+    # outside a scope the call is synchronous again
+    y, u, v = orc.synth_planes(64, 64, "noise", seed=9, amp=30)
+    out = str(tmp_path / "sync.jpeg")
+    assert lib.h2j_host_yuv2jpeg_file(y.ctypes.data, 64, u.ctypes.data, 32, v.ctypes.data, 32, 64, 64, 0, out.encode()) == 1
+    assert open(out, "rb").read() == orc.oracle_encode(y, u, v)[0]
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN_SO), reason="drop-in library not built (needs /root/reference at build time)")
+def test_dropin_batch_scope_on_the_reference_fixtures(tmp_path):
+    """The reference's own Decoder::H265ToJpeg in a loop, inside a batch scope: H.264 and H.265 inputs decoded by
+    libavcodec, queued by this repo's Encoder, encoded on the GPU as batches."""
+    lib = C.CDLL(DROPIN_SO)
+    lib.dropin_h265_to_jpeg.argtypes = [C.c_char_p, C.c_char_p]
+    lib.h2j_host_batch_end.argtypes = [C.POINTER(C.c_int)]
+    z = np.load(os.path.join(G, "ref_img_crops.npz"))
+    names = ["img01.h264", "img01.h265", "img01.h265", "img01.h264", "img01.h264"]
+    assert lib.h2j_host_batch_begin(3) == 0
+    outs = []
+    for i, name in enumerate(names):
+        out = str(tmp_path / f"{i}_{name}.jpeg")
+        assert lib.dropin_h265_to_jpeg(os.path.join(DROPIN_DIR, "fixtures", name).encode(), out.encode()) == 1
+        outs.append(out)
+    failed = C.c_int(-1)
+    assert lib.h2j_host_batch_end(C.byref(failed)) == len(names) and failed.value == 0
+    for out, name in zip(outs, names):
+        key = name.replace(".", "_")
+        assert hashlib.sha256(open(out, "rb").read()).hexdigest() == z[key + "_full_sha256"].tobytes().decode()
