@@ -227,7 +227,7 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     CU(e, cudaMemsetAsync(sl.d_zero, 0, sl.zero_bytes, st));
     {
         ScopedTiming t(e, sl, "mbvar_kernel");
-        mbvar_kernel<<<dim3(L.mcu_h, n), 128, 0, st>>>(d_frames, L, sl.d_state);
+        mbvar_kernel<<<dim3(L.mcu_h, n), 128, 0, st>>>(d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs);
         e->launches++;
     }
     const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
@@ -238,8 +238,10 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
         int tiles_per_cta = (int)((long long)n_tiles * n / ((long long)e->sm_count * 5 * 4));
         tiles_per_cta = tiles_per_cta < 1 ? 1 : (tiles_per_cta > e->fdct_tiles_per_cta ? e->fdct_tiles_per_cta : tiles_per_cta);
         if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
-        fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, 0, st>>>(
-            d_frames, L, sl.d_state, e->d_qscale_lut, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
+        static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
+        fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, extra_smem, st>>>(
+            d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }
     {
@@ -436,6 +438,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
     CUB(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
+    if (getenv("H2J_K2_EXTRA_SMEM")) CUB(cudaFuncSetAttribute(fdct_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUB(cudaFuncSetAttribute(entropy_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
 
     const int B = s->max_batch;

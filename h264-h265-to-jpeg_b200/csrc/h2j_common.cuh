@@ -89,7 +89,9 @@ struct alignas(16) FrameTab {
 // Per-frame state zeroed by one memset at the start of every batch.
 struct FrameState {
     unsigned long long var_sum;
-    unsigned long long scan_bits;   // written by the frame's last entropy tile
+    unsigned long long scan_bits;   // written by the frame's last K4b group
+    unsigned int k1_done;           // K1 CTAs that have added their share of var_sum
+    unsigned int pad_;
     unsigned int hist[4][256];      // DC luma, DC chroma, AC luma, AC chroma symbol counts (K2)
 };
 

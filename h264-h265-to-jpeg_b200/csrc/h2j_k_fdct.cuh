@@ -15,9 +15,7 @@
 // (TMA) store; the only CTA-wide barrier per tile is the one in front of that store.  Pixel rows of the next
 // tile are requested before the statistics of the current one are taken, so their latency is covered by work.
 //
-// The first CTA of a frame also publishes the rate-control result (K1's variance sum -> qscale) and the
-// quantiser tables; every CTA recomputes them for itself (64 threads, a few dozen instructions) instead of
-// waiting for a separate set-up launch.
+// The frame's qscale and quantiser tables are set up once per frame by the last CTA of K1 (h2j_k_planes.cuh).
 #pragma once
 #include "h2j_common.cuh"
 
@@ -27,22 +25,26 @@
 
 namespace h2j {
 
-// plane / position of block n (0..3 luma, 4 Cb, 5 Cr) of MCU m
-struct BlockGeom {
+// What a thread needs to know about the plane its block lives in: fixed for the whole kernel.
+struct PlaneRef {
     const uint8_t *P;
-    int pitch, pw, ph, bx, by;
+    int pitch, pw, ph;   // row pitch in bytes, width / height the encoder reads (edges are replicated beyond)
+    int step;            // block spacing per MCU: 16 luma, 8 chroma
+    int xoff, yoff;      // block offset inside the MCU
+    bool can_fast;       // rows start 8-byte aligned: 64-bit loads
 };
-__device__ __forceinline__ BlockGeom block_geom(const uint8_t *base, const FrameLayout &L, int mx, int my, int n)
+__device__ __forceinline__ PlaneRef plane_ref(const uint8_t *base, const FrameLayout &L, int n)
 {
-    BlockGeom g;
+    PlaneRef r;
     if (n < 4) {
-        g.P = base; g.pitch = L.y_pitch; g.pw = L.w; g.ph = L.h;
-        g.bx = mx * 16 + (n & 1) * 8; g.by = my * 16 + (n >> 1) * 8;
+        r.P = base; r.pitch = L.y_pitch; r.pw = L.w; r.ph = L.h; r.step = 16;
+        r.xoff = (n & 1) * 8; r.yoff = (n >> 1) * 8;
     } else {
-        g.P = base + (n == 4 ? L.u_off : L.v_off); g.pitch = L.c_pitch; g.pw = L.cw; g.ph = L.ch;
-        g.bx = mx * 8; g.by = my * 8;
+        r.P = base + (n == 4 ? L.u_off : L.v_off); r.pitch = L.c_pitch; r.pw = L.cw; r.ph = L.ch; r.step = 8;
+        r.xoff = 0; r.yoff = 0;
     }
-    return g;
+    r.can_fast = L.aligned8 != 0;
+    return r;
 }
 
 // MCU position that advances a tile (16 MCUs) at a time without dividing
@@ -67,56 +69,66 @@ struct McuPos {
 struct BlockFetch {
     uint2 rows[8];
     uint2 prow;          // lanes that help with a predecessor DC: one row of that block
-    BlockGeom g, pg;
+    int bx, by, pbx, pby;
     bool valid;          // the block exists
     bool fast;           // rows[] hold the pixels (aligned, not cut by the right edge); else they are read bytewise
     bool phelp, pfast;   // this lane adds a row of the predecessor block / prow holds it
-    int prow_idx;
 };
 
-__device__ __forceinline__ void fetch_issue(BlockFetch &F, const uint8_t *base, const FrameLayout &L, const McuPos &mp, int n, bool valid,
-                                            bool phelp, const McuPos &pp, int pn, int prow_idx)
+__device__ __forceinline__ void fetch_issue(BlockFetch &F, const PlaneRef &R, const McuPos &mp, bool valid, const PlaneRef &Q,
+                                            const McuPos &pp, bool phelp, int prow_idx)
 {
     F.valid = valid;
     F.fast = false;
     F.phelp = phelp;
     F.pfast = false;
-    F.prow_idx = prow_idx;
     if (valid) {
-        F.g = block_geom(base, L, mp.mx, mp.my, n);
-        F.fast = L.aligned8 != 0 && F.g.bx + 8 <= F.g.pw;
+        F.bx = mp.mx * R.step + R.xoff;
+        F.by = mp.my * R.step + R.yoff;
+        F.fast = R.can_fast && F.bx + 8 <= R.pw;
         if (F.fast) {
+            if (F.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
+                const uint8_t *p = R.P + (long long)F.by * R.pitch + F.bx;
 #pragma unroll
-            for (int r = 0; r < 8; r++) F.rows[r] = ldg64(F.g.P + (long long)min(F.g.by + r, F.g.ph - 1) * F.g.pitch + F.g.bx);
+                for (int r = 0; r < 8; r++) {
+                    F.rows[r] = ldg64(p);
+                    p += R.pitch;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; r++) F.rows[r] = ldg64(R.P + (long long)min(F.by + r, R.ph - 1) * R.pitch + F.bx);
+            }
         }
     }
     if (phelp) {
-        F.pg = block_geom(base, L, pp.mx, pp.my, pn);
-        F.pfast = L.aligned8 != 0 && F.pg.bx + 8 <= F.pg.pw;
-        if (F.pfast) F.prow = ldg64(F.pg.P + (long long)min(F.pg.by + prow_idx, F.pg.ph - 1) * F.pg.pitch + F.pg.bx);
+        F.pbx = pp.mx * Q.step + Q.xoff;
+        F.pby = min(pp.my * Q.step + Q.yoff + prow_idx, Q.ph - 1);
+        F.pfast = Q.can_fast && F.pbx + 8 <= Q.pw;
+        if (F.pfast) F.prow = ldg64(Q.P + (long long)F.pby * Q.pitch + F.pbx);
     }
 }
 
-__device__ __forceinline__ void fetch_consume(const BlockFetch &F, const uint8_t *lut, int (&v)[64])
+__device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRef &R, const uint8_t *lut, int (&v)[64])
 {
     if (F.fast) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            v[r * 8 + 0] = F.rows[r].x & 0xff;
-            v[r * 8 + 1] = (F.rows[r].x >> 8) & 0xff;
-            v[r * 8 + 2] = (F.rows[r].x >> 16) & 0xff;
-            v[r * 8 + 3] = F.rows[r].x >> 24;
-            v[r * 8 + 4] = F.rows[r].y & 0xff;
-            v[r * 8 + 5] = (F.rows[r].y >> 8) & 0xff;
-            v[r * 8 + 6] = (F.rows[r].y >> 16) & 0xff;
-            v[r * 8 + 7] = F.rows[r].y >> 24;
+            // one byte permute per sample (selector 4 = a zero byte of the second operand)
+            v[r * 8 + 0] = (int)__byte_perm(F.rows[r].x, 0u, 0x4440);
+            v[r * 8 + 1] = (int)__byte_perm(F.rows[r].x, 0u, 0x4441);
+            v[r * 8 + 2] = (int)__byte_perm(F.rows[r].x, 0u, 0x4442);
+            v[r * 8 + 3] = (int)__byte_perm(F.rows[r].x, 0u, 0x4443);
+            v[r * 8 + 4] = (int)__byte_perm(F.rows[r].y, 0u, 0x4440);
+            v[r * 8 + 5] = (int)__byte_perm(F.rows[r].y, 0u, 0x4441);
+            v[r * 8 + 6] = (int)__byte_perm(F.rows[r].y, 0u, 0x4442);
+            v[r * 8 + 7] = (int)__byte_perm(F.rows[r].y, 0u, 0x4443);
         }
     } else {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const uint8_t *row = F.g.P + (long long)min(F.g.by + r, F.g.ph - 1) * F.g.pitch;
+            const uint8_t *row = R.P + (long long)min(F.by + r, R.ph - 1) * R.pitch;
 #pragma unroll
-            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(F.g.bx + c, F.g.pw - 1)];
+            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(F.bx + c, R.pw - 1)];
         }
     }
     if (lut) {
@@ -126,15 +138,15 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const uint8_t
 }
 
 // this lane's share (one pixel row) of the predecessor block's sample sum
-__device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const uint8_t *lut)
+__device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const PlaneRef &Q, const uint8_t *lut)
 {
     if (!F.phelp) return 0;
     if (F.pfast && !lut) return (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
-    const uint8_t *row = F.pg.P + (long long)min(F.pg.by + F.prow_idx, F.pg.ph - 1) * F.pg.pitch;
+    const uint8_t *row = Q.P + (long long)F.pby * Q.pitch;
     int s = 0;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        const int p = row[min(F.pg.bx + c, F.pg.pw - 1)];
+        const int p = row[min(F.pbx + c, Q.pw - 1)];
         s += lut ? lut[p] : p;
     }
     return s;
@@ -142,8 +154,7 @@ __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const uint
 
 __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
                                                                      FrameState *__restrict__ state,
-                                                                     const uint8_t *__restrict__ qscale_lut,
-                                                                     FrameTab *__restrict__ tabs,
+                                                                     const FrameTab *__restrict__ tabs,
                                                                      uint32_t *__restrict__ images,  // [frame][images_cap] tile images
                                                                      long long images_cap, int tiles_per_cta)
 {
@@ -152,7 +163,6 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     __shared__ __align__(16) int s_bq[64];
     __shared__ unsigned int s_hist[2][256];
     __shared__ unsigned int s_dchist[2][16];
-    __shared__ int s_qs;
 
     const int f = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,52 +182,23 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     // predecessor block of the warp's first lane(s): luma -> Y3 of the MCU in front of the warp's eight;
     // chroma -> Cb (lanes 0-7 help) and Cr (lanes 8-15 help) of the MCU in front of the tile (first tile only)
     const bool phelp_lane = luma ? lane < 8 : lane < 16;
-    const int pn = luma ? 3 : 4 + (lane >> 3);
     const int mcu_first = luma ? warp * 8 : 0;
+    const PlaneRef R = plane_ref(base, L, n), Q = plane_ref(base, L, luma ? 3 : 4 + (lane >> 3));
 
     BlockFetch F;
     McuPos mp, pp;  // this thread's MCU / the MCU in front of the warp's range, for the tile being fetched
     mp.init(tile0 * kTileMcus + mcu_l, L.mcu_w);
     pp.init(tile0 * kTileMcus + mcu_first - 1, L.mcu_w);
-    fetch_issue(F, base, L, mp, n, mp.m < L.n_mcu, phelp_lane && pp.m >= 0 && pp.m < L.n_mcu, pp, pn, lane & 7);
+    fetch_issue(F, R, mp, mp.m < L.n_mcu, Q, pp, phelp_lane && pp.m >= 0 && pp.m < L.n_mcu, lane & 7);
 
-    // ---- rate control + quantiser set-up (ratecontrol.c first I picture, mpegvideo_enc.c encode_picture) ----
-    if (tid == 0) {
-        const long long var = (long long)state[f].var_sum;
-        int q;
-        if (L.fixed_qscale > 0) q = L.fixed_qscale;
-        else {
-            // predict_size(): the IEEE-exact part; the pow()/rounding tail is folded into qscale_lut by the host
-            const double bits = __ddiv_rn(__dmul_rn(826.0, sqrt((double)var)), 236.0);
-            int nb = (int)bits;
-            nb = nb > kQscaleLutSize - 1 ? kQscaleLutSize - 1 : (nb < 0 ? 0 : nb);
-            q = qscale_lut[nb];
-        }
-        s_qs = q;
-        if (blockIdx.x == 0) {
-            tabs[f].qscale = q;
-            tabs[f].mb_var_sum = var;
-            tabs[f].status = 0;
-        }
+    // ---- the frame's quantiser (set up once per frame by K1's last CTA), cleared statistics ----
+    if (tid < 64) {
+        const uint32_t pk = tabs[f].qpack[tid];
+        s_q[tid] = (int)(pk & 0xffffu);
+        s_bq[tid] = (int)(pk >> 16);
     }
     for (int i = tid; i < 512; i += kFdctThreads) (&s_hist[0][0])[i] = 0;
     if (tid < 32) (&s_dchist[0][0])[tid] = 0;
-    __syncthreads();
-    if (tid < 64) {
-        uint8_t m;
-        uint32_t pk;
-        quant_entry(s_qs, c_mpeg1_intra[tid], tid, &m, &pk);
-        s_q[tid] = (int)(pk & 0xffffu);
-        s_bq[tid] = (int)(pk >> 16);
-        if (blockIdx.x == 0) {
-            tabs[f].qpack[tid] = pk;
-            tabs[f].intra[tid] = m;
-            uint8_t mk;
-            uint32_t pk2;
-            quant_entry(s_qs, c_mpeg1_intra[c_zigzag[tid]], c_zigzag[tid], &mk, &pk2);  // DQT is stored in zigzag order
-            tabs[f].dqt_zz[tid] = mk;
-        }
-    }
     __syncthreads();
 
     int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
@@ -227,7 +208,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         const bool valid = F.valid;
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
-        int psum = fetch_pred_rowsum(F, lut);
+        int psum = fetch_pred_rowsum(F, Q, lut);
         psum += __shfl_xor_sync(0xffffffffu, psum, 1);
         psum += __shfl_xor_sync(0xffffffffu, psum, 2);
         psum += __shfl_xor_sync(0xffffffffu, psum, 4);
@@ -244,7 +225,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         uint32_t *rec = img + slot * kBlkWords;
         if (valid) {
             int v[64];
-            fetch_consume(F, lut, v);
+            fetch_consume(F, R, lut, v);
             fdct_8x8(v);
             dc = quant_dc(v[0]);
             // quantise without the final >> 16: the level is the upper half of the 32-bit product, so two of them
@@ -273,7 +254,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         if (tile + 1 < tile_end) {
             mp.advance(L.mcu_w);
             pp.advance(L.mcu_w);
-            fetch_issue(F, base, L, mp, n, mp.m < L.n_mcu, luma && phelp_lane && pp.m < L.n_mcu, pp, pn, lane & 7);
+            fetch_issue(F, R, mp, mp.m < L.n_mcu, Q, pp, luma && phelp_lane && pp.m < L.n_mcu, lane & 7);
         }
 
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
@@ -292,9 +273,10 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             // iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
             unsigned int *hist = s_hist[cls];
+            unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
             auto count = [&](int k, int below, int val) {
                 const int run = k - below - 1, nb = mag_bits(val);
-                if (run >= 16) atomicAdd(&hist[0xf0], (unsigned)(run >> 4));
+                zrl += (unsigned)run >> 4;
                 atomicAdd(&hist[((run & 15) << 4) | nb], 1u);
             };
             unsigned lo = mask_lo;
@@ -325,6 +307,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                 prev = k;
             }
             if (prev < 63) atomicAdd(&hist[0], 1u);
+            if (zrl) atomicAdd(&hist[0xf0], zrl);
         }
 
         // ---- the image leaves with one bulk store; the other buffer's store must have been read out by now.

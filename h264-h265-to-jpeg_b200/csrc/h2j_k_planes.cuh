@@ -8,8 +8,11 @@ namespace h2j {
 // K1: mb_var_thread (mpegvideo_enc.c) — sum over macroblocks of ((norm1 - sum^2/256 + 628) >> 8)
 // grid (mcu_h, n_frames), one thread per macroblock column, 16 independent 128-bit loads in flight.
 // ------------------------------------------------------------------------------------------------
+// The CTA that finishes a frame last (completion counter) turns the sum into the frame's qscale (ratecontrol.c first
+// I picture) and publishes the quantiser tables (mpegvideo_enc.c encode_picture + ff_convert_matrix) for K2.
 __global__ void __launch_bounds__(128) mbvar_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
-                                                    FrameState *__restrict__ state)
+                                                    FrameState *__restrict__ state, const uint8_t *__restrict__ qscale_lut,
+                                                    FrameTab *__restrict__ tabs)
 {
     const int f = blockIdx.y, my = blockIdx.x;
     const uint8_t *Y = frames + (long long)f * L.frame_stride;
@@ -51,10 +54,42 @@ __global__ void __launch_bounds__(128) mbvar_kernel(const uint8_t *__restrict__ 
     for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
     __syncthreads();
+    __shared__ int s_last, s_qs;
     if (threadIdx.x == 0) {
         long long t = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += warp_sums[i];
         atomicAdd(&state[f].var_sum, (unsigned long long)t);
+        __threadfence();
+        const unsigned done = atomicAdd(&state[f].k1_done, 1u);
+        s_last = done == gridDim.x - 1;
+        if (s_last) {
+            __threadfence();
+            const long long var = (long long)atomicAdd(&state[f].var_sum, 0ull);  // every CTA's share is in
+            int q;
+            if (L.fixed_qscale > 0) q = L.fixed_qscale;
+            else {
+                // predict_size(): the IEEE-exact part; the pow()/rounding tail is folded into qscale_lut by the host
+                const double bits = __ddiv_rn(__dmul_rn(826.0, sqrt((double)var)), 236.0);
+                int nb = (int)bits;
+                nb = nb > kQscaleLutSize - 1 ? kQscaleLutSize - 1 : (nb < 0 ? 0 : nb);
+                q = qscale_lut[nb];
+            }
+            s_qs = q;
+            tabs[f].qscale = q;
+            tabs[f].mb_var_sum = var;
+            tabs[f].status = 0;
+        }
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 64) {
+        const int i = threadIdx.x;
+        uint8_t m, mk;
+        uint32_t pk, pk2;
+        quant_entry(s_qs, c_mpeg1_intra[i], i, &m, &pk);
+        tabs[f].qpack[i] = pk;
+        tabs[f].intra[i] = m;
+        quant_entry(s_qs, c_mpeg1_intra[c_zigzag[i]], c_zigzag[i], &mk, &pk2);  // DQT is stored in zigzag order
+        tabs[f].dqt_zz[i] = mk;
     }
 }
 

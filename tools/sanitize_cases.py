@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""A handful of small encodes for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+   compute-sanitizer --tool memcheck python tools/sanitize_cases.py"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "h264-h265-to-jpeg_b200")]
+import h2j_b200
+from tests.support import oracle as orc
+
+ok = True
+cases = [(322, 242, "textured", 40, 0, 0), (131, 77, "noise", 80, 0, 0), (640, 368, "textured", 30, 0, 1), (272, 208, "noise", 127, 1, 0), (1920, 1080, "textured", 40, 0, 0)]
+for (w, h, kind, amp, fq, rm) in cases:
+    y, u, v = orc.synth_planes(w, h, kind, seed=w, amp=amp)
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=3, n_slots=2, fixed_qscale=fq, range_mode=rm, max_jpeg_bytes=8 << 20) as e:
+        frames = np.stack([orc.pack_i420(y, u, v)] * 3)
+        res = e.encode_batch(frames, w, h, slot=1)
+        one = e.yuv2jpeg(y, u, v)
+        e.convert_pad(y, u, v, 1)
+    want = orc.oracle_encode(y, u, v, fixed_qscale=fq, range_mode=rm)[0]
+    good = all(j == want for j in res.jpegs) and one == want
+    print(w, h, kind, "ok" if good else "MISMATCH", len(want))
+    ok = ok and good
+sys.exit(0 if ok else 1)
