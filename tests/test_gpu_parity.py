@@ -148,3 +148,36 @@ def test_extreme_geometries(orc, w, h):
     want, dbg, _ = orc.oracle_encode(y, u, v)
     assert info.qscale == dbg.qscale and info.scan_bits == dbg.scan_bits
     assert got == want
+
+
+def test_randomised_geometries_and_contents(orc):
+    """Seeded sweep: 48 random sizes (tiles that wrap MCU rows at every phase, partial last tiles/units, single-MCU
+    frames), random content and qscale, three frames per submit.  Byte-identical JPEGs and identical histograms."""
+    import h2j_b200
+
+    rng = np.random.default_rng(20260)
+    kinds = ["textured", "noise", "blocks", "binary", "const", "ff"]
+    with h2j_b200.Encoder(max_width=700, max_height=520, max_batch=3, n_slots=2, max_jpeg_bytes=4 << 20) as e_auto:
+        encs = {0: e_auto}
+        for case in range(48):
+            w = int(rng.integers(2, 700)); h = int(rng.integers(2, 520))
+            if case % 6 == 0:
+                w = int(rng.choice([16, 17, 31, 32, 33, 255, 256, 257, 272])); h = int(rng.choice([16, 17, 31, 33, 48]))
+            fq = int(rng.choice([0, 0, 0, 1, 2, 7, 31]))
+            if fq not in encs:
+                encs[fq] = h2j_b200.Encoder(max_width=700, max_height=520, max_batch=3, n_slots=2, fixed_qscale=fq, max_jpeg_bytes=4 << 20)
+            e = encs[fq]
+            planes = [orc.synth_planes(w, h, str(rng.choice(kinds)), seed=int(rng.integers(1 << 30)), amp=int(rng.integers(0, 128))) for _ in range(3)]
+            frames = np.stack([orc.pack_i420(*p) for p in planes])
+            slot = case & 1
+            res = e.encode_batch(frames, w, h, slot=slot)
+            assert res.status == [0, 0, 0], (case, w, h, fq)
+            for i, (y, u, v) in enumerate(planes):
+                want, dbg, _ = orc.oracle_encode(y, u, v, fixed_qscale=fq)
+                info = e.frame_info(slot, i)
+                assert info.qscale == dbg.qscale, (case, w, h, fq, i)
+                for t in range(4):
+                    assert list(info.hist[t]) == list(dbg.hist[t]), (case, w, h, fq, i, t)
+                assert res.jpegs[i] == want, (case, w, h, fq, i)
+        for e in encs.values():
+            e.close()
