@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
     }
     for (int i = tid; i < kEntWarps * kWarpWinStride; i += kEntThreads) s_win_all[i] = 0;  // while the copies are on their way
-    __syncthreads();  // barrier initialised, windows cleared
+    __syncthreads();  // barrier initialised, windows cleared (clearing only the words a unit needs, once its length is
+                      // known, executes fewer instructions but measured 1 % slower: here it hides under the copy)
 
     // ---- from here on the warp is on its own ----
     const int u = tile * kEntWarps + warp;                  // unit index inside the frame
@@ -255,9 +256,12 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     if (lane == 0) {
         pos = atomicAdd(&stage_alloc[f], nwords);
         unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
-        if ((long long)pos + nwords > stage_cap_words) tabs[f].status = -4;
     }
     pos = __shfl_sync(0xffffffffu, pos, 0);
+    // words of this unit that fit the staging buffer: all of them unless the frame overflows its output cap
+    const unsigned cap_w = (unsigned)min(stage_cap_words, (long long)0xffffffffu);
+    const unsigned n_fit = pos >= cap_w ? 0u : min(nwords, cap_w - pos);
+    if (lane == 0 && n_fit < nwords) tabs[f].status = -4;
 
     if (unit_len <= (unsigned)kWarpWinBits) {
         // ---- 2. merge the slots into the warp's window ----
@@ -281,8 +285,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         }
         __syncwarp();
         // ---- 3b. stage ----
-        for (unsigned i = lane; i < nwords; i += 32)
-            if ((long long)pos + i < stage_cap_words) st[pos + i] = win[i];
+        for (unsigned i = lane; i < n_fit; i += 32) st[pos + i] = win[i];
     } else {
         for (unsigned lo = 0; lo < unit_len; lo += kWarpWinBits) {
             const unsigned hi = min(lo + (unsigned)kWarpWinBits, unit_len);
@@ -295,9 +298,9 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
                 walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, hdc, hac, &sink);
             }
             __syncwarp();
-            const unsigned nw = (hi - lo + 31) >> 5, p0 = pos + (lo >> 5);
+            const unsigned nw = (hi - lo + 31) >> 5, w0 = lo >> 5;
             for (unsigned i = lane; i < nw; i += 32)
-                if ((long long)p0 + i < stage_cap_words) st[p0 + i] = win[i];
+                if (w0 + i < n_fit) st[pos + w0 + i] = win[i];
         }
     }
 }
