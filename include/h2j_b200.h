@@ -17,6 +17,9 @@
  *
  * All entry points return 0 (H2J_OK) or a negative h2j_status.  No CPU fallback exists: if no CUDA
  * device is usable h2j_create fails with H2J_ERR_CUDA.
+ *
+ * Threading: an h2j_encoder is not internally synchronised.  Use it from one thread at a time (or one encoder
+ * per thread); different encoders are independent.  Work of different slots of one encoder overlaps on the GPU.
  */
 #ifndef H2J_B200_H
 #define H2J_B200_H
