@@ -334,11 +334,17 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
 
     // ---- lengths of the group's units, block scan ----
     const unsigned long long rec = tid < n_here ? info[u0 + tid] : 0ull;
-    s_pos[1 + tid] = unit_pos(rec);
+    // a unit that did not fit the staging buffer gets the top bit of its position: the frame is reported, not read
+    const unsigned cap_w = (unsigned)min(stage_cap_words, (long long)0x7fffffff);
+    auto checked_pos = [&](unsigned long long r) {
+        const unsigned pos = unit_pos(r), nw = (unit_bits(r) + 31) >> 5;
+        return (pos > cap_w || nw > cap_w - pos) ? (pos | 0x80000000u) : pos;
+    };
+    s_pos[1 + tid] = checked_pos(rec);
     s_len[1 + tid] = unit_bits(rec);
     if (tid == 0) {
         const unsigned long long rp = u0 > 0 ? info[u0 - 1] : 0ull;
-        s_pos[0] = unit_pos(rp);
+        s_pos[0] = checked_pos(rp);
         s_len[0] = unit_bits(rp);
     }
     unsigned incl = unit_bits(rec);
@@ -399,6 +405,8 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     const unsigned used_end = Pend & 31;
     if (has_final && used_end) Wstop++;
     if (has_final && tid == 0) state[f].scan_bits = Pend;
+    const unsigned W_final = (has_final && used_end) ? Wstop - 1 : 0xffffffffu;  // the frame's last, partial word (if any)
+    const unsigned cap_scan = (unsigned)min(scan_cap_words, (long long)0x7fffffff);
     bool overflow = false;
     for (unsigned Q = (Wbeg >> 2) + tid; Q * 4 < Wstop; Q += kPlaceThreads) {
         unsigned v[4] = {0, 0, 0, 0};
@@ -423,8 +431,7 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             }
             const unsigned len = s_len[1 + i], pos = s_pos[1 + i], P = s_excl[i];
             const unsigned plen = s_len[i], ppos = s_pos[i];
-            // a unit (or the one in front, whose tail is needed) that did not fit the staging buffer: the frame is reported
-            if ((long long)pos + ((len + 31) >> 5) > stage_cap_words || (long long)ppos + ((plen + 31) >> 5) > stage_cap_words) {
+            if ((pos | ppos) & 0x80000000u) {  // this unit, or the one in front whose tail is needed, was not staged completely
                 overflow = true;
                 have[k] = false;
                 continue;
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
                 const unsigned a = __ldg(uw + w), b2 = (sh && w + 1 < ((len + 31) >> 5)) ? __ldg(uw + w + 1) : 0u;
                 x = __funnelshift_l(b2, a, sh);
             }
-            if (has_final && W == Wstop - 1 && used_end) {
+            if (W == W_final) {
                 // bits of the word that lie behind the stream get the 1-padding up to the byte boundary, zeros after it
                 const unsigned padn = (8 - (used_end & 7)) & 7;
                 x &= ~(0xffffffffu >> used_end);
@@ -462,13 +469,13 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             v[k] = __byte_perm(v[k], 0, 0x0123);
         }
         const unsigned W0 = Q * 4;
-        if (have[0] && have[1] && have[2] && have[3] && (long long)W0 + 4 <= scan_cap_words) {
+        if (have[0] && have[1] && have[2] && have[3] && W0 + 4 <= cap_scan) {
             *reinterpret_cast<uint4 *>(gs + W0) = make_uint4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (!have[k]) continue;
-                if ((long long)W0 + k < scan_cap_words) gs[W0 + k] = v[k];
+                if (W0 + k < cap_scan) gs[W0 + k] = v[k];
                 else overflow = true;
             }
         }

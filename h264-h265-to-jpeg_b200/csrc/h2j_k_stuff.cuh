@@ -40,12 +40,18 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
         const long long w0 = (long long)c * kChunkWords + tid * 4;
         uint4 q = make_uint4(0, 0, 0, 0);
         if (w0 < nwords && w0 + 4 <= scan_cap_words) q = *reinterpret_cast<const uint4 *>(gs + w0);
-        const unsigned wv[4] = {q.x, q.y, q.z, q.w};
+        unsigned wv[4] = {q.x, q.y, q.z, q.w};  // memory byte order == stream order: byte j is (wv[j >> 2] >> (8 * (j & 3))) & 0xff
         long long rem = nbytes - w0 * 4;  // valid bytes from here on
         const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
-        unsigned cnt = 0;
+        if (nb < 16) {  // the frame's last bytes: everything behind them counts as (and is copied as) zero
 #pragma unroll
-        for (int j = 0; j < 16; j++) cnt += (j < nb && ((wv[j >> 2] >> (8 * (j & 3))) & 0xff) == 0xff) ? 1u : 0u;
+            for (int k = 0; k < 4; k++) {
+                const int left = nb - 4 * k;
+                if (left <= 0) wv[k] = 0;
+                else if (left < 4) wv[k] &= (1u << (8 * left)) - 1u;
+            }
+        }
+        const unsigned cnt = count_ff_bytes(wv[0]) + count_ff_bytes(wv[1]) + count_ff_bytes(wv[2]) + count_ff_bytes(wv[3]);
         unsigned incl = cnt;
 #pragma unroll
         for (int ofs = 1; ofs < 32; ofs <<= 1) {
@@ -63,12 +69,29 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
         }
         // ---- expand into shared memory ----
         unsigned p = (unsigned)tid * 16 + woff + incl - cnt;
+        if (cnt == 0 && nb == 16) {
+            // no 0xFF among this thread's 16 bytes (19 threads in 20): they move as a block.  The three aligned words inside
+            // [p, p + 16) are whole ours; the 4 bytes at the ragged ends share their words with the neighbours.
+            const unsigned a = p & 3;
+            uint32_t *sw = reinterpret_cast<uint32_t *>(s_out + (p & ~3u));
+            if (a == 0) {
+                sw[0] = wv[0]; sw[1] = wv[1]; sw[2] = wv[2]; sw[3] = wv[3];
+            } else {
+                const unsigned sh = a * 8;
+                sw[1] = __funnelshift_l(wv[0], wv[1], sh);  // bytes 4-a .. 8-a of ours
+                sw[2] = __funnelshift_l(wv[1], wv[2], sh);
+                sw[3] = __funnelshift_l(wv[2], wv[3], sh);
+                for (unsigned j = 0; j < 4 - a; j++) s_out[p + j] = (uint8_t)(wv[0] >> (8 * j));
+                for (unsigned j = 0; j < a; j++) s_out[p + 16 - a + j] = (uint8_t)(wv[3] >> (8 * (4 - a + j)));
+            }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (j < nb) {
-                const unsigned byte = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
-                s_out[p++] = (uint8_t)byte;
-                if (byte == 0xff) s_out[p++] = 0;
+            for (int j = 0; j < 16; j++) {
+                if (j < nb) {
+                    const unsigned byte = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
+                    s_out[p++] = (uint8_t)byte;
+                    if (byte == 0xff) s_out[p++] = 0;
+                }
             }
         }
         __syncthreads();
