@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--e2e-slots", type=int, default=4, help="batches in flight of the host-to-host pass (overlaps H2D, kernels, D2H)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU baseline sample (0 = auto)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall time the CPU baseline sample should take")
+    ap.add_argument("--max-jpeg-bytes", type=int, default=0, help="per-frame output capacity (0 = 2 MiB, the reference's HEAP_SIZE)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -242,7 +243,8 @@ def run_ours(a):
     d_frames, fb, stride = make_frames_torch(F, w, h, dev, seed0=lo)
     torch.cuda.synchronize()
 
-    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=SB, n_slots=NS, device=local_rank, profile=True)
+    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=SB, n_slots=NS, device=local_rank, profile=True,
+                           max_jpeg_bytes=a.max_jpeg_bytes)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     for s_i, st in enumerate(streams):
         enc.set_stream(s_i, st.cuda_stream)

@@ -268,7 +268,8 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     }
     {
         ScopedTiming t(e, sl, "stuff_kernel");
-        stuff_kernel<<<dim3(e->stuff_ctas, n), kStuffThreads, 0, st>>>(sl.d_tabs, sl.d_state, sl.d_scan, e->scan_cap_words, sl.d_chunk_ff,
+        static const int stuff_ctas_env = getenv("H2J_STUFF_CTAS") ? atoi(getenv("H2J_STUFF_CTAS")) : 0;  // tuning knob
+        stuff_kernel<<<dim3(stuff_ctas_env > 0 ? stuff_ctas_env : e->stuff_ctas, n), kStuffThreads, 0, st>>>(sl.d_tabs, sl.d_state, sl.d_scan, e->scan_cap_words, sl.d_chunk_ff,
                                                                       e->chunks_cap, sl.d_out, (long long)e->out_cap);
         e->launches++;
     }

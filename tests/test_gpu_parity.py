@@ -181,3 +181,19 @@ def test_randomised_geometries_and_contents(orc):
                 assert res.jpegs[i] == want, (case, w, h, fq, i)
         for e in encs.values():
             e.close()
+
+
+def test_rate_control_beyond_the_lookup_table(orc):
+    """A 4K frame of 0/255 noise drives predict_size() past the 65,536-entry qscale table (n ~ 80,000): the clamp must be
+    exact, i.e. the rate control has saturated (qscale 25) before the table ends.  Also the largest scan in the suite."""
+    import h2j_b200
+
+    w, h = 3840, 2160
+    y, u, v = orc.synth_planes(w, h, "binary", seed=99, amp=0)
+    want, dbg, _ = orc.oracle_encode(y, u, v)
+    assert dbg.qscale == 25 and 826.0 * (dbg.mb_var_sum ** 0.5) / 236.0 > 65536
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, max_jpeg_bytes=len(want) + 65536) as e:
+        got = e.yuv2jpeg(y, u, v)
+        info = e.frame_info(0, 0)
+    assert info.qscale == 25 and info.mb_var_sum == dbg.mb_var_sum
+    assert got == want
