@@ -723,7 +723,7 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
                      cudaMemcpyDeviceToHost));
     int last_dc[3] = {128, 128, 128};
     for (int b = 0; b < sl.L.n_blocks; b++) {
-        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords * 2 + (size_t)(b % kTileBlocks) * kBlkHalf);
+        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords + (size_t)tile_rec_word(b % kTileBlocks)) * 2;
         const int n = b % 6, comp = n < 4 ? 0 : n - 3;
         last_dc[comp] += rec[0];
         out[(size_t)b * 64] = (int16_t)last_dc[comp];

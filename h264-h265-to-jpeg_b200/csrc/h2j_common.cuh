@@ -34,24 +34,43 @@ struct FrameLayout {
 };
 
 // ---- coefficient store ("tile images") -----------------------------------------------------------
-// K2 works on tiles of 16 consecutive MCUs (96 blocks, coding order).  A tile leaves K2 as one contiguous
-// image: 96 block records of 33 words each, then 96 words of high mask halves.
+// K2 works on tiles of 16 consecutive MCUs (96 blocks).  A tile leaves K2 as one contiguous image made of three
+// sub-images, one per K2 warp, so that every warp can send its part on its own (no CTA barrier in K2's tile loop):
+//   sub-image 0: the 32 luma blocks of MCUs 0..7  (record index = mcu * 4 + n)
+//   sub-image 1: the 32 luma blocks of MCUs 8..15
+//   sub-image 2: Cb of the 16 MCUs (records 0..15), Cr (records 16..31)
+// A sub-image is 32 block records of 33 words each, then 32 words of high mask halves.
 //   record word j (0..31)  low half: level j, high half: level j + 32 of the zigzag scan (this pairing lets K2
 //                          derive the non-zero mask from packed 16-bit minima); level 0 is stored as the DC
 //                          *difference* to the previous block of the same component, i.e. what gets coded
 //   record word 32         non-zero mask of levels 1..31 (bit k = level k != 0, bit 0 clear).  It also makes the
-//                          record stride odd in words, so K4's per-thread reads of "coefficient k of my block"
-//                          from the image in shared memory are bank-conflict free
-//   word 3168 + b          non-zero mask of levels 32..63 of block b
-// The image is assembled in shared memory and moved with ONE bulk (TMA) store by K2 and ONE bulk load by K4.
+//                          record stride odd in words: K2's lanes write their records without bank conflicts
+//   word 1056 + r          non-zero mask of levels 32..63 of record r
+// The image is assembled in shared memory and moved with bulk (TMA) copies: three stores of 4,352 bytes by K2, ONE
+// load of two images by K4a.
 constexpr int kTileMcus = 16;
 constexpr int kTileBlocks = kTileMcus * 6;                  // 96
 constexpr int kBlkWords = 33;
 constexpr int kBlkHalf = kBlkWords * 2;                     // 66
 constexpr int kMaskLoWord = 32;                             // inside the record
-constexpr int kMaskHiOff = kTileBlocks * kBlkWords;         // 3168
-constexpr int kTileImageWords = kMaskHiOff + kTileBlocks;   // 3264
+constexpr int kSubRecs = 32;
+constexpr int kSubMaskHiOff = kSubRecs * kBlkWords;         // 1056
+constexpr int kSubImageWords = kSubMaskHiOff + kSubRecs;    // 1088
+constexpr int kSubImageBytes = kSubImageWords * 4;          // 4352 = 272 * 16
+constexpr int kTileImageWords = 3 * kSubImageWords;         // 3264
 constexpr int kTileImageBytes = kTileImageWords * 4;        // 13056 = 816 * 16
+// block b of a tile (0..95 in coding order: Y0 Y1 Y2 Y3 Cb Cr per MCU) -> (sub-image, record)
+struct TileRec { int sub, idx; };
+__host__ __device__ inline TileRec tile_rec(int b)
+{
+    const int m = b / 6, n = b - 6 * m;
+    TileRec r;
+    if (n < 4) { r.sub = m >> 3; r.idx = (m & 7) * 4 + n; }
+    else { r.sub = 2; r.idx = (n - 4) * 16 + m; }
+    return r;
+}
+__host__ __device__ inline int tile_rec_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + r.idx * kBlkWords; }
+__host__ __device__ inline int tile_maskhi_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + kSubMaskHiOff + r.idx; }
 constexpr int kFdctThreads = kTileBlocks;
 
 constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
@@ -160,6 +179,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "memory");
 }
 
+// (at most the newest one may still be reading)
+__device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // shared -> global bulk store (TMA engine), tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
 {

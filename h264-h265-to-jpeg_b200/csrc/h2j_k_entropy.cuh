@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     const int b = u * kUnitBlocks + lane;                   // == tile * kEntBlocks + tid
     if (u * kUnitBlocks >= L.n_blocks) return;              // trailing unit of the frame's last tile: no block at all
     const bool valid = b < L.n_blocks;
-    const int img_i = tid >= kTileBlocks ? 1 : 0, rec_i = tid - img_i * kTileBlocks;
-    const uint32_t *rec = s_img + img_i * kTileImageWords + rec_i * kBlkWords;
+    const int img_i = tid >= kTileBlocks ? 1 : 0, blk_i = tid - img_i * kTileBlocks;  // K2 image, block inside it (coding order)
+    const uint32_t *rec = s_img + img_i * kTileImageWords + tile_rec_word(blk_i);
     const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
     const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
     const uint32_t *hdc = s_hdc + 16 * cls, *hac = s_hac + 256 * cls;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     unsigned mask_lo = 0, mask_hi = 0;
     if (valid) {
         mask_lo = rec[kMaskLoWord];
-        mask_hi = s_img[img_i * kTileImageWords + kMaskHiOff + rec_i];
+        mask_hi = s_img[img_i * kTileImageWords + tile_maskhi_word(blk_i)];
     }
 
     // ---- 1. the walk: bits into the private slot, length on the way ----

@@ -11,14 +11,18 @@
 // output of ff_fdct_sse2 is exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17
 // == S), so eight lanes add one pixel row each -- no second FDCT.
 //
-// The tile image (h2j_common.cuh) is assembled in one of two shared-memory buffers and leaves with a single bulk
-// (TMA) store; the only CTA-wide barrier per tile is the one in front of that store.  Pixel rows of the next
-// tile are requested before the statistics of the current one are taken, so their latency is covered by work.
+// The tile image (h2j_common.cuh) is three sub-images, one per warp.  A warp assembles its sub-image in one of its two
+// shared-memory buffers and sends it with its own bulk (TMA) store: there is no CTA-wide barrier in the tile loop.
+// Pixel rows of the next tile are requested before the statistics of the current one are taken, so their latency
+// is covered by work.
 //
 // The frame's qscale and quantiser tables are set up once per frame by the last CTA of K1 (h2j_k_planes.cuh).
 #pragma once
 #include "h2j_common.cuh"
 
+#ifndef H2J_K2_WARP_STORES
+#define H2J_K2_WARP_STORES 1  // 1: every warp stores its own sub-image, no CTA barrier in the tile loop; 0: barrier + one store
+#endif
 #ifndef H2J_FDCT_MIN_CTAS
 #define H2J_FDCT_MIN_CTAS 5  // resident CTAs per SM the register allocation is bounded for (5 -> at most 136 registers)
 #endif
@@ -178,7 +182,6 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     const bool luma = warp < 2;
     const int mcu_l = luma ? warp * 8 + (lane >> 2) : (lane & 15);
     const int n = luma ? (lane & 3) : 4 + (lane >> 4);
-    const int slot = mcu_l * 6 + n;
     const int cls = luma ? 0 : 1;
     const uint8_t *lut = L.range_mode ? c_range_lut[cls] : nullptr;
     // predecessor block of the warp's first lane(s): luma -> Y3 of the MCU in front of the warp's eight;
@@ -206,8 +209,14 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
 
     for (int tile = tile0; tile < tile_end; tile++) {
-        uint32_t *img = s_img[(tile - tile0) & 1];
+        // this warp's sub-image of the tile, in one of its two buffers; the store that used this buffer two tiles ago must
+        // have read it out (lane 0 issued it, lane 0 waits)
+        uint32_t *img = s_img[(tile - tile0) & 1] + warp * kSubImageWords;
         const bool valid = F.valid;
+#if H2J_K2_WARP_STORES
+        if (lane == 0) bulk_wait_read_but_one();
+        __syncwarp();
+#endif
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
         int psum = fetch_pred_rowsum(F, Q, lut);
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         unsigned mask_lo = 0, mask_hi = 0;
         uint32_t word0_hi = 0;
         int dc = 0;
-        uint32_t *rec = img + slot * kBlkWords;
+        uint32_t *rec = img + lane * kBlkWords;  // the lane order of every warp is its record order
         if (valid) {
             int v[64];
             fetch_consume(F, R, lut, v);
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             mask_lo = ((fa & 0xffffu) | (fb << 16)) & ~1u;  // bit 0 is the DC position: always coded, never in the mask
             mask_hi = (fa >> 16) | (fb & 0xffff0000u);
             rec[kMaskLoWord] = mask_lo;
-            img[kMaskHiOff + slot] = mask_hi;
+            img[kSubMaskHiOff + lane] = mask_hi;
         }
 
         // ---- request the next tile's pixels: nothing of this tile's 64-value block is live any more ----
@@ -312,15 +321,22 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             if (zrl) atomicAdd(&hist[0xf0], zrl);
         }
 
-        // ---- the image leaves with one bulk store; the other buffer's store must have been read out by now.
-        //      (A producer/consumer variant with named barriers, where the luma warps never wait, measured 2% SLOWER
-        //      on B200 than this plain barrier: the warps of a CTA do better in step.) ----
+        // ---- the warp's sub-image leaves with one bulk store; no other warp is involved ----
         fence_proxy_async_smem();
+#if H2J_K2_WARP_STORES
+        __syncwarp();
+        if (lane == 0)
+            bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords + warp * kSubImageWords, img, kSubImageBytes);
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncthreads();  // every warp's statistics are in
+#else
         if (tid == 0) bulk_wait_read_all();
         __syncthreads();
-        if (tid == 0) bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords, img, kTileImageBytes);
+        if (tid == 0) bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords, s_img[(tile - tile0) & 1], kTileImageBytes);
     }
     if (tid == 0) bulk_wait_all();
+#endif
 
     for (int i = tid; i < 512; i += kFdctThreads) {
         const unsigned c = (&s_hist[0][0])[i];
