@@ -251,17 +251,21 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     const unsigned off = incl - len;
     const unsigned nwords = (unit_len + 31) >> 5;
 
-    // ---- 3a. reserve the staging words (any order), record the unit ----
-    unsigned pos = 0;
-    if (lane == 0) {
-        pos = atomicAdd(&stage_alloc[f], nwords);
-        unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
-    }
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    // words of this unit that fit the staging buffer: all of them unless the frame overflows its output cap
+    // ---- 3a. reserve the staging words (any order).  The atomic's round trip (~1 us) is only awaited behind the merge. ----
+    unsigned pos_lane0 = 0;
+    if (lane == 0) pos_lane0 = atomicAdd(&stage_alloc[f], nwords);
     const unsigned cap_w = (unsigned)min(stage_cap_words, (long long)0xffffffffu);
-    const unsigned n_fit = pos >= cap_w ? 0u : min(nwords, cap_w - pos);
-    if (lane == 0 && n_fit < nwords) tabs[f].status = -4;
+    // (called once the position is needed) broadcast it, record the unit, return how many of its words fit the buffer:
+    // all of them unless the frame overflows its output cap
+    auto claim = [&](unsigned &pos) {
+        pos = __shfl_sync(0xffffffffu, pos_lane0, 0);
+        const unsigned n_fit = pos >= cap_w ? 0u : min(nwords, cap_w - pos);
+        if (lane == 0) {
+            unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
+            if (n_fit < nwords) tabs[f].status = -4;
+        }
+        return n_fit;
+    };
 
     if (unit_len <= (unsigned)kWarpWinBits) {
         // ---- 2. merge the slots into the warp's window ----
@@ -285,8 +289,12 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         }
         __syncwarp();
         // ---- 3b. stage ----
+        unsigned pos;
+        const unsigned n_fit = claim(pos);
         for (unsigned i = lane; i < n_fit; i += 32) st[pos + i] = win[i];
     } else {
+        unsigned pos;
+        const unsigned n_fit = claim(pos);
         for (unsigned lo = 0; lo < unit_len; lo += kWarpWinBits) {
             const unsigned hi = min(lo + (unsigned)kWarpWinBits, unit_len);
             __syncwarp();  // previous window fully staged
