@@ -30,8 +30,10 @@ H2J_HD void fdct_col(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &
     const int s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
     const int d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
     const int um12 = s1 - s2, up12 = s1 + s2, um03 = s0 - s3, up03 = s0 + s3;   // tm12 = um12 << 3, ...
-    const int y0 = (up03 + up12) * 8;
-    const int y4 = (up03 - up12) * 8;
+    // rows 0 and 4 leave WITHOUT their << 3: fdct_row<0>, the only consumer of these two rows, carries the factor 8 in its
+    // constants instead (exact: (a * 8) * c == a * (8 * c) modulo 2^32, and nothing here exceeds 31 bits anyway)
+    const int y0 = up03 + up12;
+    const int y4 = up03 - up12;
     const int y2 = (((um12 * (27146 * 8)) >> 16) + um03 * 8) | 1;
     const int y6 = (((um03 * (27146 * 8)) >> 16) - um12 * 8) | 1;
     const int tp65 = (((d1 + d2) * (23170 * 16)) >> 16) | 1;                     // t5, t6 carry << 4
@@ -51,13 +53,14 @@ H2J_HD void fdct_col(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &
 template <int TAB>
 H2J_HD void fdct_row(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &x6, int &x7)
 {
-    constexpr int C1 = TAB == 0 ? 22725 : TAB == 1 ? 31521 : TAB == 2 ? 29692 : 26722;
-    constexpr int C2 = TAB == 0 ? 21407 : TAB == 1 ? 29692 : TAB == 2 ? 27969 : 25172;
-    constexpr int C3 = TAB == 0 ? 19266 : TAB == 1 ? 26722 : TAB == 2 ? 25172 : 22654;
-    constexpr int C4 = TAB == 0 ? 16384 : TAB == 1 ? 22725 : TAB == 2 ? 21407 : 19266;
-    constexpr int C5 = TAB == 0 ? 12873 : TAB == 1 ? 17855 : TAB == 2 ? 16819 : 15137;
-    constexpr int C6 = TAB == 0 ? 8867 : TAB == 1 ? 12299 : TAB == 2 ? 11585 : 10426;
-    constexpr int C7 = TAB == 0 ? 4520 : TAB == 1 ? 6270 : TAB == 2 ? 5906 : 5315;
+    // TAB 0 (rows 0 and 4) is scaled by 8: fdct_col hands those two rows over without their << 3
+    constexpr int C1 = TAB == 0 ? 22725 * 8 : TAB == 1 ? 31521 : TAB == 2 ? 29692 : 26722;
+    constexpr int C2 = TAB == 0 ? 21407 * 8 : TAB == 1 ? 29692 : TAB == 2 ? 27969 : 25172;
+    constexpr int C3 = TAB == 0 ? 19266 * 8 : TAB == 1 ? 26722 : TAB == 2 ? 25172 : 22654;
+    constexpr int C4 = TAB == 0 ? 16384 * 8 : TAB == 1 ? 22725 : TAB == 2 ? 21407 : 19266;
+    constexpr int C5 = TAB == 0 ? 12873 * 8 : TAB == 1 ? 17855 : TAB == 2 ? 16819 : 15137;
+    constexpr int C6 = TAB == 0 ? 8867 * 8 : TAB == 1 ? 12299 : TAB == 2 ? 11585 : 10426;
+    constexpr int C7 = TAB == 0 ? 4520 * 8 : TAB == 1 ? 6270 : TAB == 2 ? 5906 : 5315;
     constexpr int RND = 1 << 16;
     const int a0 = x0 + x7, a1 = x1 + x6, a2 = x2 + x5, a3 = x3 + x4;
     const int b0 = x0 - x7, b1 = x1 - x6, b2 = x2 - x5, b3 = x3 - x4;
