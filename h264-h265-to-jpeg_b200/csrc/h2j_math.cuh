@@ -41,8 +41,9 @@ H2J_HD void fdct_col(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &
     const int tp465 = d3 * 8 + tm65, tm465 = d3 * 8 - tm65;
     const int tm765 = d0 * 8 - tp65, tp765 = d0 * 8 + tp65;
     const int y1 = (mulh16(tp465, 13036) + tp765) | 1;
-    const int y3 = tm765 - (mulh16(tm465, -21746) + tm465);
-    const int y5 = (mulh16(tm765, -21746) + tm765) + tm465;
+    // pmulhw(a, tg3 - 1) + a == (a * (tg3 - 1 + 65536)) >> 16 exactly (a * 65536 has no low bits): one add less each
+    const int y3 = tm765 - mulh16(tm465, 65536 - 21746);
+    const int y5 = mulh16(tm765, 65536 - 21746) + tm465;
     const int y7 = mulh16(tp765, 13036) - tp465;
     x0 = y0; x1 = y1; x2 = y2; x3 = y3; x4 = y4; x5 = y5; x6 = y6; x7 = y7;
 }
