@@ -66,8 +66,14 @@ H2J_HD void fdct_row(int &x0, int &x1, int &x2, int &x3, int &x4, int &x5, int &
     const int a0 = x0 + x7, a1 = x1 + x6, a2 = x2 + x5, a3 = x3 + x4;
     const int b0 = x0 - x7, b1 = x1 - x6, b2 = x2 - x5, b3 = x3 - x4;
     const int s03 = a0 + a3, s12 = a1 + a2, d03 = a0 - a3, d12 = a1 - a2;
-    x0 = ((s03 + s12) * C4 + RND) >> 17;
-    x4 = ((s03 - s12) * C4 + RND) >> 17;
+    if (TAB == 0) {
+        // C4 == 2^17 here, and |s03 +- s12| < 2^14 for 8-bit samples: (k * 2^17 + 2^16) >> 17 == k
+        x0 = s03 + s12;
+        x4 = s03 - s12;
+    } else {
+        x0 = ((s03 + s12) * C4 + RND) >> 17;
+        x4 = ((s03 - s12) * C4 + RND) >> 17;
+    }
     x2 = (d03 * C2 + d12 * C6 + RND) >> 17;
     x6 = (d03 * C6 - d12 * C2 + RND) >> 17;
     x1 = (b0 * C1 + b1 * C3 + b2 * C5 + b3 * C7 + RND) >> 17;
