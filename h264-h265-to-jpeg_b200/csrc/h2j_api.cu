@@ -235,12 +235,12 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
         ScopedTiming t(e, sl, "fdct_quant_kernel");
         // consecutive tiles per CTA: as many as keep the grid at four waves or more (amortises the per-CTA set-up
         // and histogram flush), at most 16
-        int tiles_per_cta = (int)((long long)n_tiles * n / ((long long)e->sm_count * 5 * 4));
+        int tiles_per_cta = (int)((long long)n_tiles * n * 3 / ((long long)e->sm_count * 16 * 4));
         tiles_per_cta = tiles_per_cta < 1 ? 1 : (tiles_per_cta > e->fdct_tiles_per_cta ? e->fdct_tiles_per_cta : tiles_per_cta);
         if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
-        fdct_quant_kernel<<<dim3((n_tiles + tiles_per_cta - 1) / tiles_per_cta, n), kFdctThreads, extra_smem, st>>>(
+        fdct_quant_kernel<<<dim3(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n), kFdctThreads, extra_smem, st>>>(
             d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }

@@ -71,7 +71,7 @@ __host__ __device__ inline TileRec tile_rec(int b)
 }
 __host__ __device__ inline int tile_rec_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + r.idx * kBlkWords; }
 __host__ __device__ inline int tile_maskhi_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + kSubMaskHiOff + r.idx; }
-constexpr int kFdctThreads = kTileBlocks;
+constexpr int kFdctThreads = 32;                           // K2: single-warp CTAs, three roles per tile
 
 constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
 constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192

@@ -1,18 +1,23 @@
 // K2: pixels -> quantised zigzag coefficients, DC differences and symbol statistics.
 //
 // One thread owns one 8x8 block with all 64 values in registers.  A tile is 16 consecutive MCUs in coding order
-// (it may wrap to the next MCU row); a CTA of three warps walks `tiles_per_cta` consecutive tiles:
-//   warp 0: the four luma blocks of MCUs 0..7   (lane = mcu * 4 + n: lane order IS coding order)
-//   warp 1: the four luma blocks of MCUs 8..15
-//   warp 2: Cb of the 16 MCUs (lanes 0-15), Cr (lanes 16-31)
+// (it may wrap to the next MCU row); `tiles_per_cta` consecutive tiles are walked by three single-warp CTAs, one per
+// role (blockIdx.x = tile group * 3 + role):
+//   role 0: the four luma blocks of MCUs 0..7   (lane = mcu * 4 + n: lane order IS coding order)
+//   role 1: the four luma blocks of MCUs 8..15
+//   role 2: Cb of the 16 MCUs (lanes 0-15), Cr (lanes 16-31)
+// A CTA is ONE warp because the warps share nothing: with three-warp CTAs the registers of a finished warp stayed
+// allocated until the slowest of the three (luma and chroma blocks differ in their number of non-zero levels) reached
+// the closing barrier -- 8.5 % of the stall samples -- and 128 registers x 96 threads fits five times per SM (15 warps),
+// while 128 x 32 fits sixteen times.
 // With this mapping every DC predictor (mjpegenc.c encode_block: the previous block of the same component) is
 // the neighbouring lane's DC, so prediction is one shuffle and the warps never wait for each other.  The first
 // lane of a run needs the block in front of the warp's range; its DC is recomputed from the pixels: the DC
 // output of ff_fdct_sse2 is exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17
 // == S), so eight lanes add one pixel row each -- no second FDCT.
 //
-// The tile image (h2j_common.cuh) is three sub-images, one per warp.  A warp assembles its sub-image in one of its two
-// shared-memory buffers and sends it with its own bulk (TMA) store: there is no CTA-wide barrier in the tile loop.
+// The tile image (h2j_common.cuh) is three sub-images, one per role.  A warp assembles its sub-image in one of its two
+// shared-memory buffers and sends it with its own bulk (TMA) store.
 // Pixel rows of the next tile are requested before the statistics of the current one are taken, so their latency
 // is covered by work.
 //
@@ -20,11 +25,8 @@
 #pragma once
 #include "h2j_common.cuh"
 
-#ifndef H2J_K2_WARP_STORES
-#define H2J_K2_WARP_STORES 1  // 1: every warp stores its own sub-image, no CTA barrier in the tile loop; 0: barrier + one store
-#endif
 #ifndef H2J_FDCT_MIN_CTAS
-#define H2J_FDCT_MIN_CTAS 5  // resident CTAs per SM the register allocation is bounded for (5 -> at most 136 registers)
+#define H2J_FDCT_MIN_CTAS 16  // resident single-warp CTAs per SM the register allocation is bounded for (16 -> 128 registers)
 #endif
 
 namespace h2j {
@@ -51,72 +53,60 @@ __device__ __forceinline__ PlaneRef plane_ref(const uint8_t *base, const FrameLa
     return r;
 }
 
-// MCU position that advances a tile (16 MCUs) at a time without dividing
-struct McuPos {
-    int m, mx, my;
-    __device__ __forceinline__ void init(int m_, int mcu_w)
+// Top-left sample of a thread's block in its plane plus the MCU index; advances a tile (16 MCUs) at a time without
+// dividing.  mx = -1, my = 0 stands for "the MCU in front of MCU 0" (never dereferenced) and advances correctly.
+struct BlockPos {
+    int m, bx, by;
+    __device__ __forceinline__ void init(int m_, const PlaneRef &R, int mcu_w)
     {
         m = m_;
-        if (m_ >= 0) { my = m_ / mcu_w; mx = m_ - my * mcu_w; }
-        else { my = 0; mx = 0; }  // "the MCU in front of MCU 0": never dereferenced
+        const int my = m_ / mcu_w, mx = m_ - my * mcu_w;  // m_ = -1: my = 0, mx = -1
+        bx = mx * R.step + R.xoff;
+        by = my * R.step + R.yoff;
     }
-    __device__ __forceinline__ void advance(int mcu_w)
+    __device__ __forceinline__ void advance(const PlaneRef &R, int mcu_w)
     {
-        if (m < 0) { init(m + kTileMcus, mcu_w); return; }
+        const int row_w = mcu_w * R.step;  // bx = mx * step + xoff with xoff < step: bx >= row_w <=> mx >= mcu_w
         m += kTileMcus;
-        mx += kTileMcus;
-        while (mx >= mcu_w) { mx -= mcu_w; my++; }
+        bx += kTileMcus * R.step;
+        while (bx >= row_w) { bx -= row_w; by += R.step; }
     }
 };
 
-// The pixel rows a thread has in flight for its block of the coming tile.
+// The pixel rows a thread has in flight for its block of the coming tile.  Whether they were requested (the block exists,
+// its rows are aligned and not cut by the right edge) is recomputed from the position where it is needed: flags kept
+// across the transform were spilled to local memory and waited for (8 % of the stall samples).
 struct BlockFetch {
     uint2 rows[8];
     uint2 prow;          // lanes that help with a predecessor DC: one row of that block
-    int bx, by, pbx, pby;
-    bool valid;          // the block exists
-    bool fast;           // rows[] hold the pixels (aligned, not cut by the right edge); else they are read bytewise
-    bool phelp, pfast;   // this lane adds a row of the predecessor block / prow holds it
 };
+__device__ __forceinline__ bool fetch_is_fast(const PlaneRef &R, int bx) { return R.can_fast && bx + 8 <= R.pw; }
 
-__device__ __forceinline__ void fetch_issue(BlockFetch &F, const PlaneRef &R, const McuPos &mp, bool valid, const PlaneRef &Q,
-                                            const McuPos &pp, bool phelp, int prow_idx)
+__device__ __forceinline__ void fetch_issue(BlockFetch &F, const PlaneRef &R, const BlockPos &bp, bool valid, const PlaneRef &Q,
+                                            const BlockPos &pp, bool phelp, int prow_idx)
 {
-    F.valid = valid;
-    F.fast = false;
-    F.phelp = phelp;
-    F.pfast = false;
     // the single row of the predecessor block goes first: issued behind the eight row loads, its address arithmetic was
     // made to wait for them (register reuse), 8 % of the kernel's stall samples
-    if (phelp) {
-        F.pbx = pp.mx * Q.step + Q.xoff;
-        F.pby = min(pp.my * Q.step + Q.yoff + prow_idx, Q.ph - 1);
-        F.pfast = Q.can_fast && F.pbx + 8 <= Q.pw;
-        if (F.pfast) F.prow = ldg64(Q.P + (long long)F.pby * Q.pitch + F.pbx);
-    }
-    if (valid) {
-        F.bx = mp.mx * R.step + R.xoff;
-        F.by = mp.my * R.step + R.yoff;
-        F.fast = R.can_fast && F.bx + 8 <= R.pw;
-        if (F.fast) {
-            if (F.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
-                const uint8_t *p = R.P + (long long)F.by * R.pitch + F.bx;
+    if (phelp && fetch_is_fast(Q, pp.bx))
+        F.prow = ldg64(Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch + pp.bx);
+    if (valid && fetch_is_fast(R, bp.bx)) {
+        if (bp.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
+            const uint8_t *p = R.P + (long long)bp.by * R.pitch + bp.bx;
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    F.rows[r] = ldg64(p);
-                    p += R.pitch;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 8; r++) F.rows[r] = ldg64(R.P + (long long)min(F.by + r, R.ph - 1) * R.pitch + F.bx);
+            for (int r = 0; r < 8; r++) {
+                F.rows[r] = ldg64(p);
+                p += R.pitch;
             }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) F.rows[r] = ldg64(R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch + bp.bx);
         }
     }
 }
 
-__device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRef &R, const uint8_t *lut, int (&v)[64])
+__device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRef &R, const BlockPos &bp, const uint8_t *lut, int (&v)[64])
 {
-    if (F.fast) {
+    if (fetch_is_fast(R, bp.bx)) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             // one byte permute per sample (selector 4 = a zero byte of the second operand)
@@ -132,9 +122,9 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRe
     } else {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const uint8_t *row = R.P + (long long)min(F.by + r, R.ph - 1) * R.pitch;
+            const uint8_t *row = R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch;
 #pragma unroll
-            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(F.bx + c, R.pw - 1)];
+            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(bp.bx + c, R.pw - 1)];
         }
     }
     if (lut) {
@@ -144,15 +134,16 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRe
 }
 
 // this lane's share (one pixel row) of the predecessor block's sample sum
-__device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const PlaneRef &Q, const uint8_t *lut)
+__device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const PlaneRef &Q, const BlockPos &pp, bool phelp, int prow_idx,
+                                                 const uint8_t *lut)
 {
-    if (!F.phelp) return 0;
-    if (F.pfast && !lut) return (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
-    const uint8_t *row = Q.P + (long long)F.pby * Q.pitch;
+    if (!phelp) return 0;
+    if (fetch_is_fast(Q, pp.bx) && !lut) return (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
+    const uint8_t *row = Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch;
     int s = 0;
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        const int p = row[min(F.pbx + c, Q.pw - 1)];
+        const int p = row[min(pp.bx + c, Q.pw - 1)];
         s += lut ? lut[p] : p;
     }
     return s;
@@ -164,17 +155,18 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                                                                      uint32_t *__restrict__ images,  // [frame][images_cap] tile images
                                                                      long long images_cap, int tiles_per_cta)
 {
-    __shared__ __align__(128) uint32_t s_img[2][kTileImageWords];
+    __shared__ __align__(128) uint32_t s_img[2][kSubImageWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
-    __shared__ unsigned int s_hist[2][256];
-    __shared__ unsigned int s_dchist[2][16];
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_dchist[16];
 
     const int f = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lane = threadIdx.x;
+    const int group = blockIdx.x / 3, warp = blockIdx.x - group * 3;  // `warp` = the role of this single-warp CTA
     const uint8_t *base = frames + (long long)f * L.frame_stride;
     const int n_tiles = (L.n_mcu + kTileMcus - 1) / kTileMcus;
-    const int tile0 = blockIdx.x * tiles_per_cta;
+    const int tile0 = group * tiles_per_cta;
     if (tile0 >= n_tiles) return;
     const int tile_end = min(tile0 + tiles_per_cta, n_tiles);
 
@@ -191,35 +183,38 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     const PlaneRef R = plane_ref(base, L, n), Q = plane_ref(base, L, luma ? 3 : 4 + (lane >> 3));
 
     BlockFetch F;
-    McuPos mp, pp;  // this thread's MCU / the MCU in front of the warp's range, for the tile being fetched
-    mp.init(tile0 * kTileMcus + mcu_l, L.mcu_w);
-    pp.init(tile0 * kTileMcus + mcu_first - 1, L.mcu_w);
-    fetch_issue(F, R, mp, mp.m < L.n_mcu, Q, pp, phelp_lane && pp.m >= 0 && pp.m < L.n_mcu, lane & 7);
+    BlockPos bp, pp;  // this thread's block / the predecessor block in front of the warp's range, for the tile being fetched
+    bp.init(tile0 * kTileMcus + mcu_l, R, L.mcu_w);
+    pp.init(tile0 * kTileMcus + mcu_first - 1, Q, L.mcu_w);
+    // lanes that add a row of the predecessor block: chroma only needs it for its first tile (then the DC is carried)
+    auto phelp_at = [&](int tile) { return phelp_lane && pp.m >= 0 && pp.m < L.n_mcu && (luma || tile == tile0); };
+    fetch_issue(F, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
 
     // ---- the frame's quantiser (set up once per frame by K1's last CTA), cleared statistics ----
-    if (tid < 64) {
-        const uint32_t pk = tabs[f].qpack[tid];
-        s_q[tid] = (int)(pk & 0xffffu);
-        s_bq[tid] = (int)(pk >> 16);
+    {
+        const uint2 pk = reinterpret_cast<const uint2 *>(tabs[f].qpack)[lane];
+        s_q[2 * lane] = (int)(pk.x & 0xffffu);
+        s_bq[2 * lane] = (int)(pk.x >> 16);
+        s_q[2 * lane + 1] = (int)(pk.y & 0xffffu);
+        s_bq[2 * lane + 1] = (int)(pk.y >> 16);
     }
-    for (int i = tid; i < 512; i += kFdctThreads) (&s_hist[0][0])[i] = 0;
-    if (tid < 32) (&s_dchist[0][0])[tid] = 0;
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) s_hist[i * 32 + lane] = 0;
+    if (lane < 16) s_dchist[lane] = 0;
+    __syncwarp();
 
     int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
 
     for (int tile = tile0; tile < tile_end; tile++) {
         // this warp's sub-image of the tile, in one of its two buffers; the store that used this buffer two tiles ago must
         // have read it out (lane 0 issued it, lane 0 waits)
-        uint32_t *img = s_img[(tile - tile0) & 1] + warp * kSubImageWords;
-        const bool valid = F.valid;
-#if H2J_K2_WARP_STORES
+        uint32_t *img = s_img[(tile - tile0) & 1];
+        const bool valid = bp.m < L.n_mcu;
         if (lane == 0) bulk_wait_read_but_one();
         __syncwarp();
-#endif
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
-        int psum = fetch_pred_rowsum(F, Q, lut);
+        int psum = fetch_pred_rowsum(F, Q, pp, phelp_at(tile), lane & 7, lut);
         psum += __shfl_xor_sync(0xffffffffu, psum, 1);
         psum += __shfl_xor_sync(0xffffffffu, psum, 2);
         psum += __shfl_xor_sync(0xffffffffu, psum, 4);
@@ -236,7 +231,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         uint32_t *rec = img + lane * kBlkWords;  // the lane order of every warp is its record order
         if (valid) {
             int v[64];
-            fetch_consume(F, R, lut, v);
+            fetch_consume(F, R, bp, lut, v);
             fdct_8x8(v);
             dc = quant_dc(v[0]);
             // quantise without the final >> 16: the level is the upper half of the 32-bit product, so two of them
@@ -263,9 +258,9 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
 
         // ---- request the next tile's pixels: nothing of this tile's 64-value block is live any more ----
         if (tile + 1 < tile_end) {
-            mp.advance(L.mcu_w);
-            pp.advance(L.mcu_w);
-            fetch_issue(F, R, mp, mp.m < L.n_mcu, Q, pp, luma && phelp_lane && pp.m < L.n_mcu, lane & 7);
+            bp.advance(R, L.mcu_w);
+            pp.advance(Q, L.mcu_w);
+            fetch_issue(F, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
@@ -276,14 +271,14 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         if (valid) {
             const int diff = dc - pred;
             rec[0] = (uint32_t)(diff & 0xffff) | word0_hi;
-            atomicAdd(&s_dchist[cls][mag_bits(diff)], 1u);
+            atomicAdd(&s_dchist[mag_bits(diff)], 1u);
             // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
             // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
             // below it and its value, so the levels can be visited in any order.  Positions 1..31 (where nearly all of
             // them are) are taken from both ends at once: two independent bit-scan -> load -> size -> atomic chains per
             // iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
-            unsigned int *hist = s_hist[cls];
+            unsigned int *hist = s_hist;
             unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
             auto count = [&](int k, int below, int val) {
                 const int run = k - below - 1, nb = mag_bits(val);
@@ -321,30 +316,25 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             if (zrl) atomicAdd(&hist[0xf0], zrl);
         }
 
-        // ---- the warp's sub-image leaves with one bulk store; no other warp is involved ----
+        // ---- the warp's sub-image leaves with one bulk store ----
         fence_proxy_async_smem();
-#if H2J_K2_WARP_STORES
         __syncwarp();
         if (lane == 0)
             bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords + warp * kSubImageWords, img, kSubImageBytes);
     }
-    if (lane == 0) bulk_wait_all();
-    __syncthreads();  // every warp's statistics are in
-#else
-        if (tid == 0) bulk_wait_read_all();
-        __syncthreads();
-        if (tid == 0) bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords, s_img[(tile - tile0) & 1], kTileImageBytes);
-    }
-    if (tid == 0) bulk_wait_all();
-#endif
+    // the stores only have to be done READING shared memory before the CTA retires; they complete on their own and the
+    // kernel boundary orders them before K4a
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
 
-    for (int i = tid; i < 512; i += kFdctThreads) {
-        const unsigned c = (&s_hist[0][0])[i];
-        if (c) atomicAdd(&state[f].hist[2 + (i >> 8)][i & 255], c);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned c = s_hist[i * 32 + lane];
+        if (c) atomicAdd(&state[f].hist[2 + cls][i * 32 + lane], c);
     }
-    if (tid < 32) {
-        const unsigned c = (&s_dchist[0][0])[tid];
-        if (c) atomicAdd(&state[f].hist[tid >> 4][tid & 15], c);
+    if (lane < 16) {
+        const unsigned c = s_dchist[lane];
+        if (c) atomicAdd(&state[f].hist[cls][lane], c);
     }
 }
 
