@@ -137,7 +137,12 @@ __device__ __forceinline__ uint2 ldg64(const uint8_t *p) { return __ldg(reinterp
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 
 // JPEG magnitude category: number of bits of |v| (0 for v == 0)
-__device__ __forceinline__ int mag_bits(int v) { return 32 - __clz(abs(v)); }
+__device__ __forceinline__ int mag_bits(int v)
+{
+    unsigned b;  // bfind gives 0xffffffff for 0: one add instead of the two that 32 - clz() compiles to
+    asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(abs(v)));
+    return (int)b + 1;
+}
 
 // number of 0xFF bytes in a 32-bit word (exact zero-byte test on the complement)
 __device__ __forceinline__ unsigned count_ff_bytes(unsigned v)

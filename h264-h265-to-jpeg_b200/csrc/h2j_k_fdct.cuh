@@ -73,53 +73,53 @@ struct BlockPos {
     }
 };
 
-// The pixel rows a thread has in flight for its block of the coming tile.  Whether they were requested (the block exists,
-// its rows are aligned and not cut by the right edge) is recomputed from the position where it is needed: flags kept
-// across the transform were spilled to local memory and waited for (8 % of the stall samples).
+// The pixel rows a thread has in flight for its block of the coming tile.  The loads are ALWAYS issued and ALWAYS unpacked
+// (blocks that do not exist, unaligned rows and rows cut by the right edge read the frame's first bytes instead and are
+// then re-read bytewise): with loads and consumers under matching branches, ptxas could not tell that the registers were
+// free again, and the first instruction touching them waited on a scoreboard shared with the load issued just before
+// (5 % of the stall samples); flags kept across the transform were spilled to local memory (8 %).
 struct BlockFetch {
     uint2 rows[8];
     uint2 prow;          // lanes that help with a predecessor DC: one row of that block
 };
 __device__ __forceinline__ bool fetch_is_fast(const PlaneRef &R, int bx) { return R.can_fast && bx + 8 <= R.pw; }
 
-__device__ __forceinline__ void fetch_issue(BlockFetch &F, const PlaneRef &R, const BlockPos &bp, bool valid, const PlaneRef &Q,
-                                            const BlockPos &pp, bool phelp, int prow_idx)
+__device__ __forceinline__ void fetch_issue(BlockFetch &F, const uint8_t *safe, const PlaneRef &R, const BlockPos &bp, bool valid,
+                                            const PlaneRef &Q, const BlockPos &pp, bool phelp, int prow_idx)
 {
-    // the single row of the predecessor block goes first: issued behind the eight row loads, its address arithmetic was
-    // made to wait for them (register reuse), 8 % of the kernel's stall samples
-    if (phelp && fetch_is_fast(Q, pp.bx))
-        F.prow = ldg64(Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch + pp.bx);
-    if (valid && fetch_is_fast(R, bp.bx)) {
-        if (bp.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
-            const uint8_t *p = R.P + (long long)bp.by * R.pitch + bp.bx;
+    const bool pf = phelp && fetch_is_fast(Q, pp.bx);
+    const bool rf = valid && fetch_is_fast(R, bp.bx);
+    const uint8_t *pq = pf ? Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch + pp.bx : safe;
+    F.prow = ldg64(pq);
+    if (!rf || bp.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
+        const uint8_t *p = rf ? R.P + (long long)bp.by * R.pitch + bp.bx : safe;
+        const int pitch = rf ? R.pitch : 0;
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                F.rows[r] = ldg64(p);
-                p += R.pitch;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 8; r++) F.rows[r] = ldg64(R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch + bp.bx);
+        for (int r = 0; r < 8; r++) {
+            F.rows[r] = ldg64(p);
+            p += pitch;
         }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; r++) F.rows[r] = ldg64(R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch + bp.bx);
     }
 }
 
 __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRef &R, const BlockPos &bp, const uint8_t *lut, int (&v)[64])
 {
-    if (fetch_is_fast(R, bp.bx)) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            // one byte permute per sample (selector 4 = a zero byte of the second operand)
-            v[r * 8 + 0] = (int)__byte_perm(F.rows[r].x, 0u, 0x4440);
-            v[r * 8 + 1] = (int)__byte_perm(F.rows[r].x, 0u, 0x4441);
-            v[r * 8 + 2] = (int)__byte_perm(F.rows[r].x, 0u, 0x4442);
-            v[r * 8 + 3] = (int)__byte_perm(F.rows[r].x, 0u, 0x4443);
-            v[r * 8 + 4] = (int)__byte_perm(F.rows[r].y, 0u, 0x4440);
-            v[r * 8 + 5] = (int)__byte_perm(F.rows[r].y, 0u, 0x4441);
-            v[r * 8 + 6] = (int)__byte_perm(F.rows[r].y, 0u, 0x4442);
-            v[r * 8 + 7] = (int)__byte_perm(F.rows[r].y, 0u, 0x4443);
-        }
-    } else {
+    for (int r = 0; r < 8; r++) {
+        // one byte permute per sample (selector 4 = a zero byte of the second operand)
+        v[r * 8 + 0] = (int)__byte_perm(F.rows[r].x, 0u, 0x4440);
+        v[r * 8 + 1] = (int)__byte_perm(F.rows[r].x, 0u, 0x4441);
+        v[r * 8 + 2] = (int)__byte_perm(F.rows[r].x, 0u, 0x4442);
+        v[r * 8 + 3] = (int)__byte_perm(F.rows[r].x, 0u, 0x4443);
+        v[r * 8 + 4] = (int)__byte_perm(F.rows[r].y, 0u, 0x4440);
+        v[r * 8 + 5] = (int)__byte_perm(F.rows[r].y, 0u, 0x4441);
+        v[r * 8 + 6] = (int)__byte_perm(F.rows[r].y, 0u, 0x4442);
+        v[r * 8 + 7] = (int)__byte_perm(F.rows[r].y, 0u, 0x4443);
+    }
+    if (!fetch_is_fast(R, bp.bx)) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const uint8_t *row = R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch;
@@ -137,14 +137,16 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRe
 __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const PlaneRef &Q, const BlockPos &pp, bool phelp, int prow_idx,
                                                  const uint8_t *lut)
 {
+    int s = (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
     if (!phelp) return 0;
-    if (fetch_is_fast(Q, pp.bx) && !lut) return (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
-    const uint8_t *row = Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch;
-    int s = 0;
+    if (!fetch_is_fast(Q, pp.bx) || lut) {
+        const uint8_t *row = Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch;
+        s = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const int p = row[min(pp.bx + c, Q.pw - 1)];
-        s += lut ? lut[p] : p;
+        for (int c = 0; c < 8; c++) {
+            const int p = row[min(pp.bx + c, Q.pw - 1)];
+            s += lut ? lut[p] : p;
+        }
     }
     return s;
 }
@@ -183,12 +185,13 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     const PlaneRef R = plane_ref(base, L, n), Q = plane_ref(base, L, luma ? 3 : 4 + (lane >> 3));
 
     BlockFetch F;
+    const uint8_t *safe = reinterpret_cast<const uint8_t *>(tabs);  // aligned, always readable: what skipped loads read
     BlockPos bp, pp;  // this thread's block / the predecessor block in front of the warp's range, for the tile being fetched
     bp.init(tile0 * kTileMcus + mcu_l, R, L.mcu_w);
     pp.init(tile0 * kTileMcus + mcu_first - 1, Q, L.mcu_w);
     // lanes that add a row of the predecessor block: chroma only needs it for its first tile (then the DC is carried)
     auto phelp_at = [&](int tile) { return phelp_lane && pp.m >= 0 && pp.m < L.n_mcu && (luma || tile == tile0); };
-    fetch_issue(F, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
+    fetch_issue(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
 
     // ---- the frame's quantiser (set up once per frame by K1's last CTA), cleared statistics ----
     {
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         if (tile + 1 < tile_end) {
             bp.advance(R, L.mcu_w);
             pp.advance(Q, L.mcu_w);
-            fetch_issue(F, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
+            fetch_issue(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
