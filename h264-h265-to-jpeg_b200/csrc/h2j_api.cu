@@ -422,7 +422,9 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
     e->units_cap = e->tiles_cap * kEntWarps;
     e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
-    e->stage_cap_words = e->scan_cap_words + e->units_cap;  // every unit starts on a word: at most one word of slack each
+    // a fixed place of one window per unit, then the reserved area for units that need more (every unit starts on a word:
+    // at most one word of slack each)
+    e->stage_cap_words = (long long)e->units_cap * kWarpWinWords + e->scan_cap_words + e->units_cap;
     e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
     e->frame_bytes_cap = align_up(tight_frame_bytes(s->max_width, s->max_height), 256);
 

@@ -8,8 +8,8 @@
 //        learns its bit length on the way (a block that needs more keeps counting and is emitted directly in 2);
 //        warp scan of the lengths.
 //     2. the slots are merged into the warp's bit window at the scanned offsets (a couple of shifted ORs per lane).
-//     3. the unit's bits, still starting at bit 0 of a word, go to a staging buffer at a position reserved with one
-//        atomicAdd (order does not matter), and (position, bit length) is recorded per unit.
+//     3. the unit's bits, still starting at bit 0 of a word, go to a staging buffer -- at the unit's own fixed place if
+//        they fit one window, else at a position reserved with an atomicAdd -- and (position, bit length) is recorded.
 //   A warp window holds 8 Kibit.  A unit that needs more (> 256 bits per block on average) takes the windowed path:
 //   direct emission clipped to one window of the unit's bit range at a time.
 //
@@ -251,13 +251,15 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     const unsigned off = incl - len;
     const unsigned nwords = (unit_len + 31) >> 5;
 
-    // ---- 3a. reserve the staging words (any order).  The atomic's round trip (~1 us) is only awaited behind the merge. ----
-    unsigned pos_lane0 = 0;
-    if (lane == 0) pos_lane0 = atomicAdd(&stage_alloc[f], nwords);
+    // ---- 3a. where the unit is staged.  A unit that fits one window (all but pathological content) owns the fixed place
+    //      u * kWarpWinWords: nothing to reserve, nothing to wait for (the atomicAdd every unit used to make was 10 % of the
+    //      kernel's stall samples although its round trip was only awaited behind the merge).  Larger units reserve their
+    //      words behind the fixed places with an atomicAdd (any order). ----
     const unsigned cap_w = (unsigned)min(stage_cap_words, (long long)0xffffffffu);
-    // (called once the position is needed) broadcast it, record the unit, return how many of its words fit the buffer:
-    // all of them unless the frame overflows its output cap
-    auto claim = [&](unsigned &pos) {
+    const unsigned fixed_words = (unsigned)units_cap * kWarpWinWords;
+    // broadcast the position, record the unit, return how many of its words fit the buffer: all of them unless the frame
+    // overflows its output cap
+    auto claim = [&](unsigned pos_lane0, unsigned &pos) {
         pos = __shfl_sync(0xffffffffu, pos_lane0, 0);
         const unsigned n_fit = pos >= cap_w ? 0u : min(nwords, cap_w - pos);
         if (lane == 0) {
@@ -289,12 +291,12 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         }
         __syncwarp();
         // ---- 3b. stage ----
-        unsigned pos;
-        const unsigned n_fit = claim(pos);
-        for (unsigned i = lane; i < n_fit; i += 32) st[pos + i] = win[i];
+        const unsigned pos = (unsigned)u * kWarpWinWords;
+        if (lane == 0) unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
+        for (unsigned i = lane; i < nwords; i += 32) st[pos + i] = win[i];
     } else {
         unsigned pos;
-        const unsigned n_fit = claim(pos);
+        const unsigned n_fit = claim(lane == 0 ? fixed_words + atomicAdd(&stage_alloc[f], nwords) : 0u, pos);
         for (unsigned lo = 0; lo < unit_len; lo += kWarpWinBits) {
             const unsigned hi = min(lo + (unsigned)kWarpWinBits, unit_len);
             __syncwarp();  // previous window fully staged
