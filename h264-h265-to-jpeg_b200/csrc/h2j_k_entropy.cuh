@@ -402,94 +402,107 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     if (tid < n_here) s_excl[tid] = s_base + warp_off + incl - unit_bits(rec);
     __syncthreads();
 
-    // ---- place: the group's output words as one flat range, four consecutive words (one 16-byte store) per thread and
-    //      step.  The unit that owns a word (the one holding its last bit) is found by bisection over the prefix table for
-    //      the first of the four and by stepping forward for the rest. ----
+    // ---- place: bit-stream concatenation, a warp per run of 32 consecutive units.  The warp walks its units in order and
+    //      carries the bits of the word that is still incomplete (c = P & 31 of them) from one unit to the next; lane l
+    //      builds the unit's l-th output word from two neighbouring staged words (coalesced loads, coalesced 4-byte
+    //      stores), and the lane behind the last complete word hands the new carry to everybody.  Only the first unit of a
+    //      run fetches its carry from the staged unit in front.  (The first form of this step gathered per output word --
+    //      bisection over the prefix table, two or three dependent scattered loads -- and was bound by their latency.) ----
     const uint32_t *st = stage + (long long)f * stage_cap_words;
     uint32_t *gs = scan + (long long)f * scan_cap_words;
     unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
     const bool has_final = u0 + n_here == n_units;
-    const unsigned P0 = s_excl[0], Pend = s_excl[n_here];
-    const unsigned Wbeg = P0 >> 5;
-    unsigned Wstop = Pend >> 5;
-    const unsigned used_end = Pend & 31;
-    if (has_final && used_end) Wstop++;
-    if (has_final && tid == 0) state[f].scan_bits = Pend;
-    const unsigned W_final = (has_final && used_end) ? Wstop - 1 : 0xffffffffu;  // the frame's last, partial word (if any)
+    if (has_final && tid == 0) state[f].scan_bits = s_excl[n_here];
     const unsigned cap_scan = (unsigned)min(scan_cap_words, (long long)0x7fffffff);
     bool overflow = false;
-    for (unsigned Q = (Wbeg >> 2) + tid; Q * 4 < Wstop; Q += kPlaceThreads) {
-        unsigned v[4] = {0, 0, 0, 0};
-        bool have[4];
-        int i = -1;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned W = Q * 4 + k;
-            have[k] = W >= Wbeg && W < Wstop;
-            if (!have[k]) continue;
-            const unsigned lastbit = min(W * 32 + 31, Pend - 1);  // (the frame's final partial word: the stream's last bit)
-            if (i < 0) {
-                int lo = 0, hi = n_here - 1;  // largest i with s_excl[i] <= lastbit
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_excl[mid] <= lastbit) lo = mid;
-                    else hi = mid - 1;
-                }
-                i = lo;
-            } else {
-                while (s_excl[i + 1] <= lastbit) i++;  // s_excl[n_here] = Pend > lastbit bounds the walk
-            }
-            const unsigned len = s_len[1 + i], pos = s_pos[1 + i], P = s_excl[i];
-            const unsigned plen = s_len[i], ppos = s_pos[i];
-            if ((pos | ppos) & 0x80000000u) {  // this unit, or the one in front whose tail is needed, was not staged completely
-                overflow = true;
-                have[k] = false;
-                continue;
-            }
-            const uint32_t *uw = st + pos;
-            // global bits [32W, 32W + 32).  Bits in front of P belong to the unit in front (a unit is never shorter than a
-            // word unless it is the frame's last, so at most two units meet in one word); the word's last bit is ours, so
-            // everything from our first bit in the word up to its end is inside this unit -- except in the frame's last word.
-            unsigned x;
-            if (W * 32 < P) {
-                const unsigned s = P - W * 32;  // 1..31 bits of the neighbour: its last s bits
+    auto emit = [&](unsigned W, unsigned x) {  // x: the word's 32 stream bits, first bit in bit 31
+        const unsigned nff = count_ff_bytes(x);
+        if (W < cap_scan) gs[W] = __byte_perm(x, 0, 0x0123);
+        else overflow = true;
+        if (nff) atomicAdd(&cff[W >> kChunkShift], nff);
+    };
+    const int ub = warp * 32, ue = min(ub + 32, n_here);
+    if (ub < ue) {
+        unsigned P = s_excl[ub], c = P & 31, carry = 0;
+        if (c) {  // the last c bits in front of P: the tail of the unit in front (never shorter than a word)
+            const unsigned plen = s_len[ub], ppos = s_pos[ub];
+            if (ppos & 0x80000000u) overflow = true;  // not staged completely: the frame is reported, not read
+            else {
                 const uint32_t *pw = st + ppos;
                 const unsigned lw = (plen - 1) >> 5, q = ((plen - 1) & 31) + 1;  // its last word and the bits used in it
                 const unsigned hiw = lw ? __ldg(pw + lw - 1) : 0u;
-                const unsigned tail = __funnelshift_r(__ldg(pw + lw), hiw, 32 - q);  // the neighbour's last 32 bits, right aligned
-                x = (tail << (32 - s)) | (__ldg(uw) >> s);
-            } else {
-                const unsigned lb = W * 32 - P, w = lb >> 5, sh = lb & 31;
-                // sh != 0: bit lb + 31 lies in word w + 1, which is ours unless this is the frame's last, partial word
-                const unsigned a = __ldg(uw + w), b2 = (sh && w + 1 < ((len + 31) >> 5)) ? __ldg(uw + w + 1) : 0u;
-                x = __funnelshift_l(b2, a, sh);
-            }
-            if (W == W_final) {
-                // bits of the word that lie behind the stream get the 1-padding up to the byte boundary, zeros after it
-                const unsigned padn = (8 - (used_end & 7)) & 7;
-                x &= ~(0xffffffffu >> used_end);
-                x |= ((1u << padn) - 1u) << (32 - used_end - padn);
-            }
-            v[k] = x;
-        }
-        unsigned c = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (have[k]) c += count_ff_bytes(v[k]);
-            v[k] = __byte_perm(v[k], 0, 0x0123);
-        }
-        const unsigned W0 = Q * 4;
-        if (have[0] && have[1] && have[2] && have[3] && W0 + 4 <= cap_scan) {
-            *reinterpret_cast<uint4 *>(gs + W0) = make_uint4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (!have[k]) continue;
-                if (W0 + k < cap_scan) gs[W0 + k] = v[k];
-                else overflow = true;
+                const unsigned tail = __funnelshift_r(__ldg(pw + lw), hiw, 32 - q);  // its last 32 bits, right aligned
+                carry = tail & ((1u << c) - 1u);
             }
         }
-        if (c) atomicAdd(&cff[W0 >> kChunkShift], c);  // the four words share a chunk
+        // A unit's first 64 staged words (256 bytes: natural content rarely has more) are loaded up front, one or two per
+        // lane, for TWO units at a time: nothing a unit needs from memory depends on the unit in front (its carry-in only
+        // touches word 0), so four loads per lane are in flight instead of one round trip after the other.
+        struct Unit {
+            const uint32_t *uw;
+            unsigned len, nw, a0, a1;
+            bool staged;
+        };
+        auto fetch = [&](int i, Unit &U) {
+            U.len = 0; U.nw = 0; U.a0 = 0; U.a1 = 0; U.staged = true; U.uw = st;
+            if (i >= ue) return;
+            const unsigned pos = s_pos[1 + i];
+            U.len = s_len[1 + i];
+            U.staged = !(pos & 0x80000000u);
+            if (!U.staged) { overflow = true; return; }
+            U.uw = st + pos;
+            U.nw = (U.len + 31) >> 5;  // staged words (the last one zero padded)
+            if ((unsigned)lane < U.nw) U.a0 = __ldg(U.uw + lane);
+            if ((unsigned)lane + 32 < U.nw) U.a1 = __ldg(U.uw + 32 + lane);
+        };
+        // virtual word k of a unit = the c carried bits + unit bits [32k - c, 32k - c + 32); the first n = (c + len) >> 5 of
+        // them are complete output words, word n holds the (c + len) & 31 bits the unit leaves open
+        auto place = [&](const Unit &U) {
+            if (U.len == 0) return;
+            const unsigned Wfirst = P >> 5;
+            const unsigned n = (c + U.len) >> 5, c2 = (c + U.len) & 31;
+            unsigned open_word;
+            {
+                const unsigned up = __shfl_up_sync(0xffffffffu, U.a0, 1);
+                const unsigned prv = lane ? up : carry;
+                const unsigned x = c ? (prv << (32 - c)) | (U.a0 >> c) : U.a0;
+                if ((unsigned)lane < n) emit(Wfirst + lane, x);
+                open_word = __shfl_sync(0xffffffffu, x, (int)(n & 31));
+            }
+            if (n >= 32) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, U.a1, 1), last0 = __shfl_sync(0xffffffffu, U.a0, 31);
+                const unsigned prv = lane ? up : last0;
+                const unsigned x = c ? (prv << (32 - c)) | (U.a1 >> c) : U.a1;
+                if ((unsigned)lane + 32 < n) emit(Wfirst + 32 + lane, x);
+                open_word = __shfl_sync(0xffffffffu, x, (int)(n & 31));
+                for (unsigned k0 = 64; k0 <= n; k0 += 32) {  // long units: straight from memory
+                    const unsigned k = k0 + lane;
+                    unsigned xx = 0;
+                    if (k <= n) {
+                        const unsigned cur = k < U.nw ? __ldg(U.uw + k) : 0u;
+                        const unsigned prv = k - 1 < U.nw ? __ldg(U.uw + k - 1) : 0u;
+                        xx = c ? (prv << (32 - c)) | (cur >> c) : cur;
+                        if (k < n) emit(Wfirst + k, xx);
+                    }
+                    open_word = __shfl_sync(0xffffffffu, xx, (int)(n & 31));
+                }
+            }
+            carry = c2 ? open_word >> (32 - c2) : 0u;
+            c = c2;
+            P += U.len;
+        };
+        for (int i = ub; i < ue; i += 2) {
+            Unit A, B;
+            fetch(i, A);
+            fetch(i + 1, B);
+            place(A);
+            place(B);
+        }
+        if (has_final && ue == n_here && c && lane == 0) {
+            // the frame's last, partial word: 1-padding up to the byte boundary (put_bits / picture trailer), zeros after it
+            const unsigned padn = (8 - (c & 7)) & 7;
+            emit(P >> 5, (carry << (32 - c)) | (((1u << padn) - 1u) << (32 - c - padn)));
+        }
     }
     if (overflow) tabs[f].status = -4;
 }

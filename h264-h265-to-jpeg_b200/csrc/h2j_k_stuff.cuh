@@ -1,33 +1,57 @@
 // K5: ff_mjpeg_escape_FF + picture trailer.  The scan of a frame is cut into chunks of 1024 words; K4 left the
 // number of 0xFF bytes of every chunk in chunk_ff, so a chunk's output position is known from a short sum and
-// chunks are independent: grid (ctas per frame, frames), each CTA strides over the frame's chunks.  A chunk is
-// expanded into shared memory (every byte, and a 0x00 after each 0xFF) and leaves as aligned 32-bit stores.
+// chunks are independent: grid (ctas per frame, frames), each CTA strides over the frame's chunks.
+//
+// A chunk is expanded in shared memory and leaves as aligned 16-byte stores:
+//   * a thread takes 16 input bytes (one 128-bit load); a block scan of the 0xFF counts gives every thread its place;
+//   * each of its four words is ONE item: the word itself, or -- with a 0x00 inserted behind each 0xFF -- up to eight
+//     bytes, ORed into the pre-zeroed image at its byte offset (two or three shared-memory atomics, no byte loop);
+//   * the image starts at the byte offset the chunk's output has inside its 16-byte line in global memory, so image
+//     quads and output quads coincide: one LDS.128 + one STG.128 per 16 bytes, bytewise only for the two ragged ends.
 // The CTA that owns the last chunk appends EOI and publishes the frame's size.
+// (The first form of this kernel expanded byte by byte whenever ANY lane of the warp had a 0xFF -- 86 % of the warps --
+// and realigned the image with funnel shifts on the way out: 39 thread instructions per byte; this one needs about 8.)
 #pragma once
 #include "h2j_common.cuh"
 
 namespace h2j {
+
+constexpr int kStuffImageWords = (2 * kChunkWords * 4 + 64) / 4;  // worst case: every byte 0xFF, plus the line offset, quad aligned
+static_assert(kStuffThreads * 4 == kChunkWords, "one 128-bit load per thread and chunk");
+
+// OR the bytes of (hi:lo) -- stream order = little-endian byte order -- into the zeroed image at byte offset q
+__device__ __forceinline__ void stuff_put(unsigned int *img, unsigned q, unsigned lo, unsigned hi)
+{
+    const unsigned s = (q & 3u) * 8u;
+    unsigned int *w = img + (q >> 2);
+    const unsigned x0 = lo << s, x1 = __funnelshift_l(lo, hi, s), x2 = s ? hi >> (32u - s) : 0u;
+    if (x0) atomicOr(w, x0);
+    if (x1) atomicOr(w + 1, x1);
+    if (x2) atomicOr(w + 2, x2);
+}
 
 __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restrict__ tabs, const FrameState *__restrict__ state,
                                                               const uint32_t *__restrict__ scan, long long scan_cap_words,
                                                               const unsigned int *__restrict__ chunk_ff, int chunks_cap,
                                                               uint8_t *__restrict__ out, long long out_cap)
 {
-    __shared__ __align__(16) uint8_t s_out[2 * kChunkWords * 4 + 32];
+    __shared__ __align__(16) unsigned int s_img[kStuffImageWords];
     __shared__ unsigned s_warp[kStuffThreads / 32];
     __shared__ unsigned s_red[kStuffThreads / 32];
 
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     FrameTab *T = tabs + f;
-    const long long bits = (long long)state[f].scan_bits;
-    const long long nbytes = (bits + 7) >> 3;
-    const long long nwords = (nbytes + 3) >> 2;
+    // bit positions are 32-bit: h2j_create bounds max_jpeg_bytes to 256 MiB
+    const unsigned bits = (unsigned)state[f].scan_bits;
+    const unsigned nbytes = (bits + 7u) >> 3;
+    const unsigned nwords = (nbytes + 3u) >> 2;
     const int nchunks = (int)((nwords + kChunkWords - 1) >> kChunkShift);
-    const long long hdr = T->header_bytes;
+    const unsigned hdr = (unsigned)T->header_bytes;
+    const unsigned cap = (unsigned)min(out_cap, (long long)0xffffffffu);
+    const unsigned scan_cap = (unsigned)min(scan_cap_words, (long long)0xffffffffu);
     const uint32_t *gs = scan + (long long)f * scan_cap_words;
     const unsigned int *cff = chunk_ff + (long long)f * chunks_cap;
     uint8_t *o = out + (long long)f * out_cap;
-    const uint32_t *s_out_w = reinterpret_cast<const uint32_t *>(s_out);
 
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         // ---- 0xFF bytes in front of this chunk ----
@@ -37,12 +61,11 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
         for (int ofs = 16; ofs; ofs >>= 1) part += __shfl_xor_sync(0xffffffffu, part, ofs);
         if (lane == 0) s_red[warp] = part;
         // ---- this thread's 4 words ----
-        const long long w0 = (long long)c * kChunkWords + tid * 4;
+        const unsigned w0 = (unsigned)c * kChunkWords + tid * 4;
         uint4 q = make_uint4(0, 0, 0, 0);
-        if (w0 < nwords && w0 + 4 <= scan_cap_words) q = *reinterpret_cast<const uint4 *>(gs + w0);
+        if (w0 < nwords && w0 + 4 <= scan_cap) q = *reinterpret_cast<const uint4 *>(gs + w0);
         unsigned wv[4] = {q.x, q.y, q.z, q.w};  // memory byte order == stream order: byte j is (wv[j >> 2] >> (8 * (j & 3))) & 0xff
-        long long rem = nbytes - w0 * 4;  // valid bytes from here on
-        const int nb = rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0);
+        const int nb = w0 * 4 + 16 <= nbytes ? 16 : (nbytes > w0 * 4 ? (int)(nbytes - w0 * 4) : 0);  // valid bytes of the 16
         if (nb < 16) {  // the frame's last bytes: everything behind them counts as (and is copied as) zero
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -51,7 +74,14 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
                 else if (left < 4) wv[k] &= (1u << (8 * left)) - 1u;
             }
         }
-        const unsigned cnt = count_ff_bytes(wv[0]) + count_ff_bytes(wv[1]) + count_ff_bytes(wv[2]) + count_ff_bytes(wv[3]);
+        unsigned ffm[4];  // 0x80 in every byte that is 0xFF
+        unsigned cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned x = ~wv[k];
+            ffm[k] = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+            cnt += __popc(ffm[k]);
+        }
         unsigned incl = cnt;
 #pragma unroll
         for (int ofs = 1; ofs < 32; ofs <<= 1) {
@@ -59,6 +89,8 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
             if (lane >= ofs) incl += t;
         }
         if (lane == 31) s_warp[warp] = incl;
+        // ---- clear the image (the previous chunk's copy-out finished behind the barrier that closes the loop body) ----
+        for (int i = tid; i < kStuffImageWords / 4; i += kStuffThreads) reinterpret_cast<uint4 *>(s_img)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         unsigned woff = 0, chunk_total = 0, before = 0;
 #pragma unroll
@@ -67,55 +99,48 @@ __global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restri
             chunk_total += s_warp[k];
             before += s_red[k];
         }
-        // ---- expand into shared memory ----
-        unsigned p = (unsigned)tid * 16 + woff + incl - cnt;
-        if (cnt == 0 && nb == 16) {
-            // no 0xFF among this thread's 16 bytes (19 threads in 20): they move as a block.  The three aligned words inside
-            // [p, p + 16) are whole ours; the 4 bytes at the ragged ends share their words with the neighbours.
-            const unsigned a = p & 3;
-            uint32_t *sw = reinterpret_cast<uint32_t *>(s_out + (p & ~3u));
-            if (a == 0) {
-                sw[0] = wv[0]; sw[1] = wv[1]; sw[2] = wv[2]; sw[3] = wv[3];
-            } else {
-                const unsigned sh = a * 8;
-                sw[1] = __funnelshift_l(wv[0], wv[1], sh);  // bytes 4-a .. 8-a of ours
-                sw[2] = __funnelshift_l(wv[1], wv[2], sh);
-                sw[3] = __funnelshift_l(wv[2], wv[3], sh);
-                for (unsigned j = 0; j < 4 - a; j++) s_out[p + j] = (uint8_t)(wv[0] >> (8 * j));
-                for (unsigned j = 0; j < a; j++) s_out[p + 16 - a + j] = (uint8_t)(wv[3] >> (8 * (4 - a + j)));
-            }
-        } else {
+        const unsigned dst0 = hdr + (unsigned)c * (kChunkWords * 4) + before;  // the chunk's first output byte
+        const unsigned a0 = (unsigned)((uintptr_t)(o + dst0) & 15u);              // ... and its offset in its 16-byte line
+        // ---- expand: one item per word ----
+        unsigned p = a0 + (unsigned)tid * 16 + woff + incl - cnt;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j < nb) {
-                    const unsigned byte = (wv[j >> 2] >> (8 * (j & 3))) & 0xff;
-                    s_out[p++] = (uint8_t)byte;
-                    if (byte == 0xff) s_out[p++] = 0;
+        for (int k = 0; k < 4; k++) {
+            unsigned lo = wv[k], hi = 0, y = ffm[k], ins = 0;
+            while (y) {  // a 0x00 behind every 0xFF (one word in 64 has one)
+                const unsigned at = ((unsigned)(__ffs((int)y) - 1) >> 3) + 1 + ins;  // byte index the zero goes to: 1..7
+                y &= y - 1;
+                const unsigned long long e = ((unsigned long long)hi << 32) | lo, m = (1ull << (8 * at)) - 1ull;
+                const unsigned long long e2 = (e & m) | ((e & ~m) << 8);
+                lo = (unsigned)e2;
+                hi = (unsigned)(e2 >> 32);
+                ins++;
+            }
+            stuff_put(s_img, p, lo, hi);
+            p += 4 + ins;
+        }
+        __syncthreads();
+        // ---- copy out: image byte a0 + i is output byte dst0 + i ----
+        const unsigned chunk_bytes_in = min((unsigned)kChunkWords * 4, nbytes - (unsigned)c * (kChunkWords * 4));
+        const unsigned end_i = a0 + chunk_bytes_in + chunk_total;  // image bytes [a0, end_i) are the chunk's output
+        uint8_t *line0 = o + dst0 - a0;                              // 16-byte aligned
+        const unsigned room = cap > dst0 - a0 ? cap - (dst0 - a0) : 0u;  // image bytes that still fit the frame's output
+        for (unsigned qi = tid; qi * 16 < end_i; qi += kStuffThreads) {
+            const uint4 v = reinterpret_cast<const uint4 *>(s_img)[qi];
+            const unsigned b0 = qi * 16;
+            if (b0 >= a0 && b0 + 16 <= end_i && b0 + 16 <= room) {
+                *reinterpret_cast<uint4 *>(line0 + b0) = v;
+            } else {
+                const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const unsigned b = b0 + j;
+                    if (b >= a0 && b < end_i && b < room) line0[b] = (uint8_t)(vv[j >> 2] >> (8 * (j & 3)));
                 }
             }
         }
-        __syncthreads();
-        // ---- copy out: dst is byte aligned at best, so head bytes, aligned words, tail bytes ----
-        const long long chunk_bytes_in = min((long long)kChunkWords * 4, nbytes - (long long)c * kChunkWords * 4);
-        const long long total = chunk_bytes_in + chunk_total;
-        const long long dst0 = hdr + (long long)c * kChunkWords * 4 + before;
-        const int head = (int)min(total, (long long)((4 - (dst0 & 3)) & 3));
-        if (tid < head && dst0 + tid < out_cap) o[dst0 + tid] = s_out[tid];
-        const long long nw = (total - head) >> 2;
-        uint32_t *ow = reinterpret_cast<uint32_t *>(o + dst0 + head);
-        for (long long i = tid; i < nw; i += kStuffThreads) {
-            const int s = head + (int)i * 4;
-            const uint32_t lo = s_out_w[s >> 2], hi = s_out_w[(s >> 2) + 1];
-            if (dst0 + head + i * 4 + 4 <= out_cap) ow[i] = __funnelshift_r(lo, hi, (s & 3) * 8);
-        }
-        const int tail = (int)((total - head) & 3);
-        if (tid < tail) {
-            const long long at = dst0 + head + nw * 4 + tid;
-            if (at < out_cap) o[at] = s_out[head + nw * 4 + tid];
-        }
         if (c == nchunks - 1 && tid == 0) {
             const long long ff = (long long)before + chunk_total;
-            const long long end = hdr + nbytes + ff;
+            const long long end = (long long)hdr + nbytes + ff;
             if (end + 2 <= out_cap) { o[end] = 0xff; o[end + 1] = 0xd9; }
             else T->status = -4;
             T->scan_bits = bits;
