@@ -246,7 +246,7 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     }
     {
         ScopedTiming t(e, sl, "huffman_kernel");
-        huffman_kernel<<<n, kHuffThreads, 4 * sizeof(HuffScratch), st>>>(L, sl.d_tabs, sl.d_state, sl.d_out, (long long)e->out_cap,
+        huffman_kernel<<<4 * n, kHuffGroup, 0, st>>>(L, sl.d_tabs, sl.d_state, n, sl.d_out, (long long)e->out_cap,
                                                                        e->d_comment, (int)e->comment.size());
         e->launches++;
     }
@@ -440,7 +440,6 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMalloc(&e->d_comment, e->comment.size() + 1));
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
-    CUB(cudaFuncSetAttribute(huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(HuffScratch))));
     if (getenv("H2J_K2_EXTRA_SMEM")) CUB(cudaFuncSetAttribute(fdct_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUB(cudaFuncSetAttribute(entropy_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
 

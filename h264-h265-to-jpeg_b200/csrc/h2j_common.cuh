@@ -110,7 +110,7 @@ struct FrameState {
     unsigned long long var_sum;
     unsigned long long scan_bits;   // written by the frame's last K4b group
     unsigned int k1_done;           // K1 CTAs that have added their share of var_sum
-    unsigned int pad_;
+    unsigned int k3_done;           // K3 CTAs (one per table) that have finished: the fourth writes the header
     unsigned int hist[4][256];      // DC luma, DC chroma, AC luma, AC chroma symbol counts (K2)
 };
 

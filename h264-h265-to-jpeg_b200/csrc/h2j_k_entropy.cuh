@@ -52,6 +52,10 @@ constexpr int kSlotBits = kSlotWords * 32;
 constexpr int kSlotStride = kSlotWords + 1;                  // odd stride: the lanes' word i never share a bank
 constexpr int kPlaceGroupUnits = 256;                        // K4b: units per CTA, one per thread
 constexpr int kPlaceThreads = 256;
+#ifndef H2J_PLACE_BATCH
+#define H2J_PLACE_BATCH 4
+#endif
+constexpr int kPlaceBatch = H2J_PLACE_BATCH;                   // K4b: units whose staged words a warp requests before it places them
 
 // per-unit record written by K4a: where the unit's bits were staged and how many there are
 __device__ __forceinline__ unsigned long long unit_pack(unsigned pos_words, unsigned bits) { return ((unsigned long long)pos_words << 32) | bits; }
@@ -436,52 +440,50 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             }
         }
         // A unit's first 64 staged words (256 bytes: natural content rarely has more) are loaded up front, one or two per
-        // lane, for TWO units at a time: nothing a unit needs from memory depends on the unit in front (its carry-in only
-        // touches word 0), so four loads per lane are in flight instead of one round trip after the other.
-        struct Unit {
-            const uint32_t *uw;
-            unsigned len, nw, a0, a1;
-            bool staged;
-        };
-        auto fetch = [&](int i, Unit &U) {
-            U.len = 0; U.nw = 0; U.a0 = 0; U.a1 = 0; U.staged = true; U.uw = st;
+        // lane, for kPlaceBatch units at a time: nothing a unit needs from memory depends on the unit in front (its
+        // carry-in only touches word 0), so 2 * kPlaceBatch loads per lane are in flight instead of one round trip after
+        // the other.
+        auto fetch = [&](int i, unsigned &a0, unsigned &a1) {
+            a0 = 0; a1 = 0;
             if (i >= ue) return;
-            const unsigned pos = s_pos[1 + i];
-            U.len = s_len[1 + i];
-            U.staged = !(pos & 0x80000000u);
-            if (!U.staged) { overflow = true; return; }
-            U.uw = st + pos;
-            U.nw = (U.len + 31) >> 5;  // staged words (the last one zero padded)
-            if ((unsigned)lane < U.nw) U.a0 = __ldg(U.uw + lane);
-            if ((unsigned)lane + 32 < U.nw) U.a1 = __ldg(U.uw + 32 + lane);
+            const unsigned pos = s_pos[1 + i], nw = (s_len[1 + i] + 31) >> 5;  // staged words (the last one zero padded)
+            if (pos & 0x80000000u) return;
+            const uint32_t *uw = st + pos;
+            if ((unsigned)lane < nw) a0 = __ldg(uw + lane);
+            if ((unsigned)lane + 32 < nw) a1 = __ldg(uw + 32 + lane);
         };
         // virtual word k of a unit = the c carried bits + unit bits [32k - c, 32k - c + 32); the first n = (c + len) >> 5 of
         // them are complete output words, word n holds the (c + len) & 31 bits the unit leaves open
-        auto place = [&](const Unit &U) {
-            if (U.len == 0) return;
+        auto place = [&](int i, unsigned a0, unsigned a1) {
+            if (i >= ue) return;
+            const unsigned pos = s_pos[1 + i], len = s_len[1 + i];
+            const bool staged = !(pos & 0x80000000u);
+            if (!staged) overflow = true;  // not staged completely: the frame is reported, not read
             const unsigned Wfirst = P >> 5;
-            const unsigned n = (c + U.len) >> 5, c2 = (c + U.len) & 31;
+            const unsigned n = (c + len) >> 5, c2 = (c + len) & 31;
             unsigned open_word;
             {
-                const unsigned up = __shfl_up_sync(0xffffffffu, U.a0, 1);
+                const unsigned up = __shfl_up_sync(0xffffffffu, a0, 1);
                 const unsigned prv = lane ? up : carry;
-                const unsigned x = c ? (prv << (32 - c)) | (U.a0 >> c) : U.a0;
+                const unsigned x = c ? (prv << (32 - c)) | (a0 >> c) : a0;
                 if ((unsigned)lane < n) emit(Wfirst + lane, x);
                 open_word = __shfl_sync(0xffffffffu, x, (int)(n & 31));
             }
             if (n >= 32) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, U.a1, 1), last0 = __shfl_sync(0xffffffffu, U.a0, 31);
+                const unsigned up = __shfl_up_sync(0xffffffffu, a1, 1), last0 = __shfl_sync(0xffffffffu, a0, 31);
                 const unsigned prv = lane ? up : last0;
-                const unsigned x = c ? (prv << (32 - c)) | (U.a1 >> c) : U.a1;
+                const unsigned x = c ? (prv << (32 - c)) | (a1 >> c) : a1;
                 if ((unsigned)lane + 32 < n) emit(Wfirst + 32 + lane, x);
                 open_word = __shfl_sync(0xffffffffu, x, (int)(n & 31));
+                const uint32_t *uw = st + (staged ? pos : 0u);
+                const unsigned nw = staged ? (len + 31) >> 5 : 0u;
                 for (unsigned k0 = 64; k0 <= n; k0 += 32) {  // long units: straight from memory
                     const unsigned k = k0 + lane;
                     unsigned xx = 0;
                     if (k <= n) {
-                        const unsigned cur = k < U.nw ? __ldg(U.uw + k) : 0u;
-                        const unsigned prv = k - 1 < U.nw ? __ldg(U.uw + k - 1) : 0u;
-                        xx = c ? (prv << (32 - c)) | (cur >> c) : cur;
+                        const unsigned cur = k < nw ? __ldg(uw + k) : 0u;
+                        const unsigned prv2 = k - 1 < nw ? __ldg(uw + k - 1) : 0u;
+                        xx = c ? (prv2 << (32 - c)) | (cur >> c) : cur;
                         if (k < n) emit(Wfirst + k, xx);
                     }
                     open_word = __shfl_sync(0xffffffffu, xx, (int)(n & 31));
@@ -489,14 +491,14 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             }
             carry = c2 ? open_word >> (32 - c2) : 0u;
             c = c2;
-            P += U.len;
+            P += len;
         };
-        for (int i = ub; i < ue; i += 2) {
-            Unit A, B;
-            fetch(i, A);
-            fetch(i + 1, B);
-            place(A);
-            place(B);
+        for (int i = ub; i < ue; i += kPlaceBatch) {
+            unsigned a0[kPlaceBatch], a1[kPlaceBatch];
+#pragma unroll
+            for (int j = 0; j < kPlaceBatch; j++) fetch(i + j, a0[j], a1[j]);
+#pragma unroll
+            for (int j = 0; j < kPlaceBatch; j++) place(i + j, a0[j], a1[j]);
         }
         if (has_final && ue == n_here && c && lane == 0) {
             // the frame's last, partial word: 1-padding up to the byte boundary (put_bits / picture trailer), zeros after it

@@ -1,5 +1,5 @@
 // K3: optimal Huffman tables (mjpegenc_huffman.c) + code tables + JPEG header (mjpegenc_common.c).
-// One CTA per frame, four groups of 128 threads, one group per table (DC luma, DC chroma, AC luma, AC chroma).
+// One CTA of 128 threads per table (DC luma, DC chroma, AC luma, AC chroma) and frame.
 //
 // What is sequential and why: AV_QSORT is not stable and the order of equal counts / equal lengths decides the
 // DHT bytes, so both sorts are replayed step for step by one thread of the group (in shared memory).
@@ -47,9 +47,37 @@ __device__ void av_qsort_pairs(HuffPair *p, int num)
                 }
                 if (start == end - 2) break;
                 H2J_SWAP(end[-1], *mid);
+                // The two scans below visit the elements in the reference's order and stop where it stops; only the LOADS
+                // differ: four keys are requested at once (the walk is a chain of shared-memory round trips otherwise --
+                // this thread is the frame's critical path).  Reading past `right` / below `left` is harmless: the keys
+                // are only looked at under the reference's own bounds test, and the addresses stay inside the array
+                // (start <= left, right <= end - 2, elements up to p[num + 2] exist).
+                const int pivot = end[-1].b;  // end[-1] is not touched inside the partition loop
                 while (left <= right) {
-                    while (left <= right && H2J_CMP(left, end - 1) < 0) left++;
-                    while (left <= right && H2J_CMP(right, end - 1) > 0) right--;
+                    for (;;) {
+                        const int k0 = left[0].b, k1 = left[1].b, k2 = left[2].b, k3 = left[3].b;
+                        if (!(left <= right && k0 < pivot)) break;
+                        left++;
+                        if (!(left <= right && k1 < pivot)) break;
+                        left++;
+                        if (!(left <= right && k2 < pivot)) break;
+                        left++;
+                        if (!(left <= right && k3 < pivot)) break;
+                        left++;
+                    }
+                    for (;;) {
+                        HuffPair *r1 = right - 1 < start ? start : right - 1, *r2 = right - 2 < start ? start : right - 2,
+                                 *r3 = right - 3 < start ? start : right - 3;
+                        const int k0 = right[0].b, k1 = r1->b, k2 = r2->b, k3 = r3->b;
+                        if (!(left <= right && k0 > pivot)) break;
+                        right--;
+                        if (!(left <= right && k1 > pivot)) break;
+                        right--;
+                        if (!(left <= right && k2 > pivot)) break;
+                        right--;
+                        if (!(left <= right && k3 > pivot)) break;
+                        right--;
+                    }
                     if (left <= right) {
                         H2J_SWAP(*left, *right);
                         left++;
@@ -293,21 +321,31 @@ __device__ uint8_t header_byte(int i, const HeaderPlan &h, const FrameTab *T, co
     return tail[k];
 }
 
-__global__ void __launch_bounds__(kHuffThreads) huffman_kernel(FrameLayout L, FrameTab *__restrict__ tabs, const FrameState *__restrict__ state,
-                                                               uint8_t *__restrict__ out, long long out_cap,
-                                                               const char *__restrict__ comment, int comment_len)
+// grid 4 * frames CTAs of one group each: one table per CTA.  blockIdx.x / frames picks the table, AC tables first (they
+// take ~10x longer than the DC ones and decide the kernel's duration: with one CTA per FRAME the four scratch areas
+// allowed two CTAs per SM, and 512 frames needed two waves of them).  The frame's CTA that finishes last writes the header.
+__global__ void __launch_bounds__(kHuffGroup) huffman_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
+                                                             int n_frames, uint8_t *__restrict__ out, long long out_cap,
+                                                             const char *__restrict__ comment, int comment_len)
 {
-    extern __shared__ __align__(16) unsigned char huff_smem[];
-    HuffScratch *scratch = reinterpret_cast<HuffScratch *>(huff_smem);
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int group = tid / kHuffGroup, gt = tid % kHuffGroup;
+    __shared__ HuffScratch scratch;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x / n_frames, f = blockIdx.x - slot * n_frames;
+    const int table = slot ^ 2;  // 2, 3 (AC luma, AC chroma), then 0, 1 (DC)
     FrameTab *T = tabs + f;
-    build_one_table(state[f].hist[group], scratch + group, gt, group, T->bits[group], T->vals[group], &T->nvals[group], T->hcode[group]);
+    build_one_table(state[f].hist[table], &scratch, tid, 0, T->bits[table], T->vals[table], &T->nvals[table], T->hcode[table]);
+    __threadfence();
     __syncthreads();
-    // the tables were written to global memory by other threads of this CTA: __syncthreads orders them for us
-    const HeaderPlan h = header_plan(T->nvals, comment_len);
+    if (tid == 0) s_last = atomicAdd(&state[f].k3_done, 1u) == 3u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();  // the other three tables were written by other CTAs
+    const volatile int *nv = T->nvals;
+    const int nvals[4] = {nv[0], nv[1], nv[2], nv[3]};
+    const HeaderPlan h = header_plan(nvals, comment_len);
     uint8_t *o = out + (long long)f * out_cap;
-    for (int i = tid; i < h.total; i += kHuffThreads)
+    for (int i = tid; i < h.total; i += kHuffGroup)
         if (i < out_cap) o[i] = header_byte(i, h, T, L, comment, comment_len);
     if (tid == 0) {
         T->header_bytes = h.total;

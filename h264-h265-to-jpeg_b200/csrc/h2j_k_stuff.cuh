@@ -30,7 +30,7 @@ __device__ __forceinline__ void stuff_put(unsigned int *img, unsigned q, unsigne
     if (x2) atomicOr(w + 2, x2);
 }
 
-__global__ void __launch_bounds__(kStuffThreads) stuff_kernel(FrameTab *__restrict__ tabs, const FrameState *__restrict__ state,
+__global__ void __launch_bounds__(kStuffThreads, 8) stuff_kernel(FrameTab *__restrict__ tabs, const FrameState *__restrict__ state,
                                                               const uint32_t *__restrict__ scan, long long scan_cap_words,
                                                               const unsigned int *__restrict__ chunk_ff, int chunks_cap,
                                                               uint8_t *__restrict__ out, long long out_cap)
