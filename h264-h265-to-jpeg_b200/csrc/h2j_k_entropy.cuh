@@ -14,13 +14,14 @@
 //   direct emission clipped to one window of the unit's bit range at a time.
 //
 // K4b scan_place_kernel -- turns the staged units into the frame's bit stream (0.25 MB per 1080p frame):
-//   A CTA takes a group of 64 consecutive units through an atomic ticket, scans their bit lengths, publishes the
+//   A CTA takes a group of 256 consecutive units through an atomic ticket, scans their bit lengths, publishes the
 //   group total and resolves the group's exclusive prefix with a decoupled look-back over the frame's earlier
 //   groups (one 64-bit descriptor per group: [63:62] status 0 invalid / 1 group total / 2 inclusive prefix,
-//   [61:0] bits).  Every unit is then shifted to its global bit position and stored as big-endian words; a 32-bit
-//   word is written by the unit that holds its last bit, with the leading bits fetched from the staged unit in
-//   front.  No atomics on the scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are counted
-//   into per-chunk counters for K5; the frame's last word is padded with ones (put_bits / picture trailer).
+//   [61:0] bits).  Each warp then concatenates a run of 32 units at their global bit positions: a 32-bit word is
+//   written (big-endian) by the unit that holds its last bit, the bits of the word that is still open are carried to
+//   the next unit, and only a run's first unit fetches its carry from the staged unit in front.  No atomics on the
+//   scan, no pre-zeroed output.  While storing, the 0xFF bytes of every word are counted into per-chunk counters for
+//   K5; the frame's last word is padded with ones (put_bits / picture trailer).
 #pragma once
 #include <cstddef>
 
