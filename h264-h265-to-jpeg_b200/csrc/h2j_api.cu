@@ -505,6 +505,39 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     return H2J_OK;
 }
 
+int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int pitch, size_t uv_offset, int n,
+                           int width, int height)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    Slot &sl = e->slots[slot];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
+    if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
+    if (width < 2 || height < 2) return fail(e, H2J_ERR_UNSUPPORTED, "unsupported frame size %dx%d", width, height);
+    const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
+    if (pitch < width || pitch < 2 * fcw) return fail(e, H2J_ERR_INVALID_ARG, "pitch %d smaller than a row of %d samples", pitch, width);
+    if (uv_offset < (size_t)pitch * height || frame_stride < uv_offset + (size_t)pitch * (fch - 1) + 2 * (size_t)fcw)
+        return fail(e, H2J_ERR_INVALID_ARG, "uv_offset / frame_stride do not hold an NV12 frame of %dx%d at pitch %d", width, height, pitch);
+    const size_t fb = tight_frame_bytes(width, height);
+    const size_t dstride = align_up(fb, 256);
+    if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
+    CU(e, cudaSetDevice(e->s.device));
+    rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
+    if (rc) return rc;
+    sl.n = n;
+    CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
+    const int src_aligned16 = ((uintptr_t)d_frames % 16) == 0 && (frame_stride % 16) == 0 && (pitch % 16) == 0 ? 1 : 0;
+    const int row_bytes = width > 2 * fcw ? width : 2 * fcw;
+    nv12_to_i420_kernel<<<dim3((row_bytes + 128 * 16 - 1) / (128 * 16), height + fch, n), 128, 0, sl.stream>>>(
+        d_frames, (long long)frame_stride, pitch, (long long)uv_offset, sl.d_frames, sl.L, src_aligned16);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    rc = launch_pipeline(e, sl, sl.d_frames, n, false);
+    if (rc) return rc;
+    sl.busy = true;
+    return H2J_OK;
+}
+
 int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t frame_stride, int n, int width, int height)
 {
     int rc = check_slot(e, slot);

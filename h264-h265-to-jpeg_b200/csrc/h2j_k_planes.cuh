@@ -134,4 +134,44 @@ __global__ void __launch_bounds__(128) convert_pad_kernel(const uint8_t *__restr
     if (x0 + 8 < padw) o2[1] = make_uint2(w[2], w[3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// NV12 (what hardware decoders produce: a luma plane and ONE plane of interleaved Cb/Cr pairs, both with a row pitch)
+// -> the tight I420 frames the pipeline reads.  grid (x, rows, frames): rows 0..h-1 copy luma, rows h..h+ch-1 split a
+// chroma row.  16 bytes per thread where pitch, base and width allow, bytes otherwise.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) nv12_to_i420_kernel(const uint8_t *__restrict__ src, long long src_stride, int pitch, long long uv_off,
+                                                           uint8_t *__restrict__ dst, FrameLayout L, int src_aligned16)
+{
+    const int f = blockIdx.z, row = blockIdx.y;
+    const uint8_t *S = src + (long long)f * src_stride;
+    uint8_t *D = dst + (long long)f * L.frame_stride;
+    const int fch = (L.h + 1) >> 1;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (row < L.h) {
+        if (x0 >= L.w) return;
+        const uint8_t *s = S + (long long)row * pitch + x0;
+        uint8_t *d = D + (long long)row * L.y_pitch + x0;
+        if (src_aligned16 && L.aligned16 && x0 + 16 <= L.w) *reinterpret_cast<uint4 *>(d) = ldg128(s);
+        else
+            for (int i = 0; i < 16 && x0 + i < L.w; i++) d[i] = s[i];
+    } else if (row < L.h + fch) {
+        const int r = row - L.h;
+        if (x0 >= 2 * L.c_pitch) return;  // c_pitch = ceil(w / 2) pairs per row
+        const uint8_t *s = S + uv_off + (long long)r * pitch + x0;
+        uint8_t *du = D + L.u_off + (long long)r * L.c_pitch + (x0 >> 1), *dv = D + L.v_off + (long long)r * L.c_pitch + (x0 >> 1);
+        if (src_aligned16 && (uv_off & 15) == 0 && L.aligned8 && x0 + 16 <= 2 * L.c_pitch) {
+            const uint4 v = ldg128(s);
+            const unsigned u0 = __byte_perm(v.x, v.y, 0x6420), u1 = __byte_perm(v.z, v.w, 0x6420);
+            const unsigned w0 = __byte_perm(v.x, v.y, 0x7531), w1 = __byte_perm(v.z, v.w, 0x7531);
+            *reinterpret_cast<uint2 *>(du) = make_uint2(u0, u1);
+            *reinterpret_cast<uint2 *>(dv) = make_uint2(w0, w1);
+        } else {
+            for (int i = 0; i < 8 && (x0 >> 1) + i < L.c_pitch; i++) {
+                du[i] = s[2 * i];
+                dv[i] = s[2 * i + 1];
+            }
+        }
+    }
+}
+
 }  // namespace h2j

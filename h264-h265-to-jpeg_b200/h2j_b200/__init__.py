@@ -72,7 +72,7 @@ class FrameInfo(C.Structure):
 
 EXPORTS = [
     "h2j_default_settings", "h2j_create", "h2j_destroy", "h2j_last_error", "h2j_status_string", "h2j_abi_version",
-    "h2j_encode_frame", "h2j_submit_host", "h2j_submit_device", "h2j_collect", "h2j_collect_device", "h2j_wait",
+    "h2j_encode_frame", "h2j_submit_host", "h2j_submit_device", "h2j_submit_device_nv12", "h2j_collect", "h2j_collect_device", "h2j_wait",
     "h2j_alloc_pinned", "h2j_free_pinned", "h2j_convert_pad", "h2j_debug_frame_info", "h2j_debug_coefficients",
     "h2j_slot_kernel_ms", "h2j_slot_total_ms", "h2j_kernel_launches", "h2j_slot_set_stream",
 ]
@@ -105,6 +105,7 @@ def load_library() -> C.CDLL:
     lib.h2j_encode_frame.argtypes = [vp, C.POINTER(vp), C.POINTER(ci), ci, ci, vp, sz, C.POINTER(sz)]
     lib.h2j_submit_host.argtypes = [vp, ci, vp, sz, ci, ci, ci]
     lib.h2j_submit_device.argtypes = [vp, ci, vp, sz, ci, ci, ci]
+    lib.h2j_submit_device_nv12.argtypes = [vp, ci, vp, sz, ci, sz, ci, ci, ci]
     lib.h2j_collect.argtypes = [vp, ci, vp, sz, C.POINTER(sz), C.POINTER(ci)]
     lib.h2j_collect_device.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
     lib.h2j_wait.argtypes = [vp, ci]
@@ -253,6 +254,12 @@ class Encoder:
 
     def submit_device(self, slot: int, d_frames_ptr: int, frame_stride: int, n: int, width: int, height: int) -> None:
         self._check(self._lib.h2j_submit_device(self._h, slot, d_frames_ptr, frame_stride, n, width, height))
+        self._n_in_slot[slot] = n
+
+    def submit_device_nv12(self, slot: int, d_frames_ptr: int, frame_stride: int, pitch: int, uv_offset: int, n: int,
+                           width: int, height: int) -> None:
+        """NV12 frames in device memory (luma plane + interleaved Cb/Cr plane, rows `pitch` apart)."""
+        self._check(self._lib.h2j_submit_device_nv12(self._h, slot, d_frames_ptr, frame_stride, pitch, uv_offset, n, width, height))
         self._n_in_slot[slot] = n
 
     def set_stream(self, slot: int, cuda_stream: int) -> None:

@@ -106,6 +106,14 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
                     int height);
 int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int n, int width,
                       int height);
+/* h2j_submit_device_nv12: the batch is NV12 in device memory, as hardware decoders (NVDEC) leave it: per frame a luma
+ * plane of `height` rows and, `uv_offset` bytes behind the frame's start, a plane of ceil(height/2) rows of interleaved
+ * Cb/Cr pairs; both planes have rows `pitch` bytes apart, frames are `frame_stride` bytes apart.  The pairs are split
+ * into the slot's own I420 frame buffer by one extra kernel and the batch proceeds as in h2j_submit_device; the JPEGs are
+ * the ones the reference writes for the equivalent yuv420p frame (the reference itself has no NV12 input: its decoder is
+ * libavcodec's software decoder, src/Decoder.cpp:183, :324-342).  Collect with h2j_collect / h2j_collect_device. */
+int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int pitch,
+                           size_t uv_offset, int n, int width, int height);
 int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, size_t *offsets, int *status);
 int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *d_frame_capacity, size_t *sizes,
                        int *status);

@@ -44,4 +44,27 @@ for (w, h) in ((1920, 1080), (3840, 2160)):
             j = e.yuv2jpeg(y, u, v)
         dt = (time.perf_counter() - t0) / 20
     res[f"single_frame_{w}x{h}"] = {"ms_host_to_host": round(dt * 1e3, 3), "jpeg_bytes": len(j)}
+
+# NV12 device input (NVDEC layout: pitch 2048, chroma plane behind 1088 luma rows), 256 x 1080p
+def nv12_throughput(w, h, n, pitch, rows, reps=5):
+    d, fb, stride = make_frames_torch(min(n, 32), w, h, dev)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    k = d.shape[0]
+    nv = torch.zeros((k, pitch * (rows + ch)), dtype=torch.uint8, device=dev)
+    nv[:, : pitch * h].view(k, h, pitch)[:, :, :w] = d[:, : w * h].view(k, h, w)
+    uvv = nv[:, pitch * rows :].view(k, ch, pitch)
+    uvv[:, :, 0 : 2 * cw : 2] = d[:, w * h : w * h + cw * ch].view(k, ch, cw)
+    uvv[:, :, 1 : 2 * cw : 2] = d[:, w * h + cw * ch : w * h + 2 * cw * ch].view(k, ch, cw)
+    nv = nv.repeat((n + k - 1) // k, 1)[:n].contiguous()
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=n, n_slots=1) as e:
+        for _ in range(2):
+            e.submit_device_nv12(0, nv.data_ptr(), nv.shape[1], pitch, pitch * rows, n, w, h); e.collect_device(0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(reps):
+            e.submit_device_nv12(0, nv.data_ptr(), nv.shape[1], pitch, pitch * rows, n, w, h); e.collect_device(0)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / reps
+    return n / dt, dt * 1e3
+
+fps, ms = nv12_throughput(1920, 1080, 256, 2048, 1088)
+res["nv12_1080p_batch256"] = {"frames_per_s": round(fps), "ms_per_batch": round(ms, 3)}
 print(json.dumps(res, indent=1))
