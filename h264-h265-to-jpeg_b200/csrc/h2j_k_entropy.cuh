@@ -421,10 +421,11 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     const unsigned cap_scan = (unsigned)min(scan_cap_words, (long long)0x7fffffff);
     bool overflow = false;
     auto emit = [&](unsigned W, unsigned x) {  // x: the word's 32 stream bits, first bit in bit 31
-        const unsigned nff = count_ff_bytes(x);
-        if (W < cap_scan) gs[W] = __byte_perm(x, 0, 0x0123);
-        else overflow = true;
-        if (nff) atomicAdd(&cff[W >> kChunkShift], nff);
+        if (W < cap_scan) {  // (words behind the frame's capacity are dropped: the frame is reported, K5 never reads them)
+            gs[W] = __byte_perm(x, 0, 0x0123);
+            const unsigned nff = count_ff_bytes(x);
+            if (nff) atomicAdd(&cff[W >> kChunkShift], nff);
+        } else overflow = true;
     };
     const int ub = warp * 32, ue = min(ub + 32, n_here);
     if (ub < ue) {

@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kStuffThreads, 8) stuff_kernel(FrameTab *__res
     const unsigned bits = (unsigned)state[f].scan_bits;
     const unsigned nbytes = (bits + 7u) >> 3;
     const unsigned nwords = (nbytes + 3u) >> 2;
-    const int nchunks = (int)((nwords + kChunkWords - 1) >> kChunkShift);
+    // a frame that outgrew its capacity (reported by K4b, status -4) is cut at the capacity: nothing behind it exists
+    const int nchunks = min((int)((nwords + kChunkWords - 1) >> kChunkShift), chunks_cap);
     const unsigned hdr = (unsigned)T->header_bytes;
     const unsigned cap = (unsigned)min(out_cap, (long long)0xffffffffu);
     const unsigned scan_cap = (unsigned)min(scan_cap_words, (long long)0xffffffffu);

@@ -21,4 +21,22 @@ for (w, h, kind, amp, fq, rm) in cases:
     good = all(j == want for j in res.jpegs) and one == want
     print(w, h, kind, "ok" if good else "MISMATCH", len(want))
     ok = ok and good
+# NV12 device input and a frame whose scan is dense with 0xFF bytes (stuffing) / has units larger than a window
+import torch
+w, h = 322, 242
+y, u, v = orc.synth_planes(w, h, "ff", seed=5)
+cw, ch = (w + 1) // 2, (h + 1) // 2
+pitch = 336
+nv = np.zeros(pitch * (h + ch), np.uint8)
+nv[: pitch * h].reshape(h, pitch)[:, :w] = y
+uvp = nv[pitch * h:].reshape(ch, pitch)
+uvp[:, 0:2 * cw:2] = u
+uvp[:, 1:2 * cw:2] = v
+d = torch.from_numpy(nv).cuda()
+with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, max_jpeg_bytes=8 << 20) as e:
+    e.submit_device_nv12(0, d.data_ptr(), nv.size, pitch, pitch * h, 1, w, h)
+    got = e.collect(0).jpegs[0]
+good = got == orc.oracle_encode(y, u, v)[0]
+print("nv12 ff", "ok" if good else "MISMATCH")
+ok = ok and good
 sys.exit(0 if ok else 1)
