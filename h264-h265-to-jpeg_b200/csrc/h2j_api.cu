@@ -766,6 +766,13 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     return H2J_OK;
 }
 
+int h2j_set_profile(h2j_encoder *e, int on)
+{
+    if (!e) return H2J_ERR_INVALID_ARG;
+    e->s.profile = on ? 1 : 0;
+    return H2J_OK;
+}
+
 int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, int cap)
 {
     int rc = check_slot(e, slot);

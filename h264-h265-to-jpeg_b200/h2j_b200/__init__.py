@@ -74,7 +74,7 @@ EXPORTS = [
     "h2j_default_settings", "h2j_create", "h2j_destroy", "h2j_last_error", "h2j_status_string", "h2j_abi_version",
     "h2j_encode_frame", "h2j_submit_host", "h2j_submit_device", "h2j_submit_device_nv12", "h2j_collect", "h2j_collect_device", "h2j_wait",
     "h2j_alloc_pinned", "h2j_free_pinned", "h2j_convert_pad", "h2j_debug_frame_info", "h2j_debug_coefficients",
-    "h2j_slot_kernel_ms", "h2j_slot_total_ms", "h2j_kernel_launches", "h2j_slot_set_stream",
+    "h2j_slot_kernel_ms", "h2j_set_profile", "h2j_slot_total_ms", "h2j_kernel_launches", "h2j_slot_set_stream",
 ]
 
 _lib = None
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     lib.h2j_debug_frame_info.argtypes = [vp, ci, ci, C.POINTER(FrameInfo)]
     lib.h2j_debug_coefficients.argtypes = [vp, ci, ci, vp, sz]
     lib.h2j_slot_kernel_ms.argtypes = [vp, ci, C.POINTER(C.c_char_p), C.POINTER(C.c_float), ci]
+    lib.h2j_set_profile.argtypes = [vp, ci]
     lib.h2j_slot_total_ms.argtypes = [vp, ci, C.POINTER(C.c_float)]
     lib.h2j_kernel_launches.argtypes = [vp]
     lib.h2j_kernel_launches.restype = C.c_longlong
@@ -261,6 +262,10 @@ class Encoder:
         """NV12 frames in device memory (luma plane + interleaved Cb/Cr plane, rows `pitch` apart)."""
         self._check(self._lib.h2j_submit_device_nv12(self._h, slot, d_frames_ptr, frame_stride, pitch, uv_offset, n, width, height))
         self._n_in_slot[slot] = n
+
+    def set_profile(self, on: bool) -> None:
+        """Per-kernel event brackets for the batches submitted from now on."""
+        self._check(self._lib.h2j_set_profile(self._h, 1 if on else 0))
 
     def set_stream(self, slot: int, cuda_stream: int) -> None:
         """Enqueue the slot's work on a caller-owned stream (raw cudaStream_t handle)."""

@@ -159,6 +159,9 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
 /* With settings.profile != 0: milliseconds each kernel of the slot's last batch took, measured with CUDA
  * events on the stream the kernels were launched on.  names/ms have `cap` entries; returns the count. */
 int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, int cap);
+/* Switch the per-kernel event brackets of batches submitted from now on (settings.profile at run time): a bracket
+ * costs a few microseconds of idle GPU per kernel boundary, so throughput runs take them on a sample of their batches. */
+int h2j_set_profile(h2j_encoder *e, int on);
 /* Milliseconds between the first and the last event of the slot's last batch (includes copies). */
 int h2j_slot_total_ms(h2j_encoder *e, int slot, float *ms);
 /* Number of kernel launches issued by this encoder so far. */
