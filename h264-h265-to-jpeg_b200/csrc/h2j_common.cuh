@@ -73,7 +73,10 @@ __host__ __device__ inline int tile_rec_word(int b) { const TileRec r = tile_rec
 __host__ __device__ inline int tile_maskhi_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + kSubMaskHiOff + r.idx; }
 constexpr int kFdctThreads = 32;                           // K2: single-warp CTAs, three roles per tile
 
-constexpr int kEntFdctTiles = 2;                            // K4 tile = 2 K2 tiles
+#ifndef H2J_ENT_FDCT_TILES
+#define H2J_ENT_FDCT_TILES 1
+#endif
+constexpr int kEntFdctTiles = H2J_ENT_FDCT_TILES;            // K2 tiles per K4a CTA: 1 (0.749 ms at 512 x 1080p) against 2 (0.775 ms)
 constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192
 constexpr int kEntThreads = kEntBlocks;
 constexpr int kMaxBitsPerBlock = 27 * 64;                   // DC (16+11) + 63 * (16+11); ZRLs only replace coefficients

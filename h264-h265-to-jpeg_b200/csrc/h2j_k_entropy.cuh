@@ -1,9 +1,9 @@
 // K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame), in two kernels.
 //
 // K4a entropy_walk_kernel -- all the coding work, no dependency between CTAs or warps:
-//   A CTA takes a tile of 192 consecutive blocks of one frame (two K2 tile images) and pulls the images (levels
+//   A CTA takes kEntFdctTiles K2 tiles of one frame (one: 96 consecutive blocks) and pulls the tile image (levels
 //   and non-zero masks) and the frame's code tables into shared memory with bulk copies (cp.async.bulk -> SASS
-//   UBLKCP) signalled on an mbarrier.  Each of the six warps then works alone on its UNIT of 32 blocks:
+//   UBLKCP) signalled on an mbarrier.  Each of the CTA's warps then works alone on its UNIT of 32 blocks:
 //     1. ONE walk over the block: every lane encodes its block into a private 256-bit slot in shared memory and
 //        learns its bit length on the way (a block that needs more keeps counting and is emitted directly in 2);
 //        warp scan of the lengths.
@@ -44,7 +44,7 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 }
 
 constexpr int kUnitBlocks = 32;                              // one warp
-constexpr int kEntWarps = kEntThreads / 32;                  // 6 units per tile
+constexpr int kEntWarps = kEntThreads / 32;                  // units per CTA
 constexpr int kWarpWinWords = 256;                           // per-warp bit window: 8 Kibit
 constexpr int kWarpWinBits = kWarpWinWords * 32;
 constexpr int kWarpWinStride = kWarpWinWords + 4;            // spare words for the last partial OR
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
                                                                    uint32_t *__restrict__ stage, long long stage_cap_words)
 {
     extern __shared__ __align__(128) unsigned char ent_smem[];
-    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                    // two tile images
+    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                    // the CTA's tile images
     uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [2][16] DC code tables
     uint32_t *s_hac = s_hdc + 32;                                                                // [2][256] AC code tables
     unsigned int *s_win_all = s_hac + 512;                                                       // [warp][kWarpWinStride]
