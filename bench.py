@@ -102,22 +102,70 @@ def make_frames_numpy(n, w, h, seed0=0):
 # clocks
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML is polled from a thread every couple of milliseconds
+    (the timed region of the default run lasts ~30 ms: `nvidia-smi -lms` does not even start up in that time, which is
+    what an 8-GPU run showed); `nvidia-smi` stays as the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.h = None
         self.p = None
+        self.f = None
+        self.thread = None
+        self.samples = []
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(gpu_index)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.h is not None:
+            import threading
+
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": "nvml"}
+            nv = self.nv
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+            reasons = sorted({n for _, r in self.samples for n, bit in names if r & bit})
+            return {"sm_mhz": float(np.median([m for m, _ in self.samples])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(self.samples), "source": "nvml, polled every 2 ms during the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -140,8 +188,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
-
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -375,6 +422,16 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t.item())
     value = world * F * a.steps / (dev_ms_max / 1000.0)
+    if world > 1:  # every rank's own time and clock, so that a slow GPU (power cap, clocks) shows in the line
+        g = torch.zeros(world, 2, device=dev)
+        g[rank, 0] = dev_ms
+        g[rank, 1] = clocks.get("sm_mhz") or 0.0
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        flags = torch.zeros(world, device=dev)
+        flags[rank] = 1.0 if clocks.get("reasons") and clocks["reasons"] != ["no samples"] else 0.0
+        dist.all_reduce(flags, op=dist.ReduceOp.SUM)
+        clocks["per_rank"] = {"ms_timed_region": [round(float(x), 3) for x in g[:, 0].tolist()], "sm_mhz": [float(x) for x in g[:, 1].tolist()],
+                              "ranks_with_throttle_reasons": [i for i, x in enumerate(flags.tolist()) if x > 0]}
 
     # ---- informational: the same job with two half-batches in flight on two streams ------------------
     # (the HBM-bound K1 and the latency-bound K3 of one half run under the issue-bound kernels of the other; not the
