@@ -50,6 +50,8 @@ struct Slot {
     long long *h_sizes = nullptr;             // pinned (jpeg_bytes per frame)
     uint8_t *h_stage = nullptr;               // pinned staging for h2j_encode_frame / convert
     size_t h_stage_bytes = 0;
+    unsigned char *h_tail = nullptr;          // pinned: status .. jpeg_bytes of frame 0's FrameTab (h2j_encode_frame)
+    size_t spec_bytes = 384 * 1024;           // JPEG bytes h2j_encode_frame copies back before it knows the size
     bool busy = false;
     bool own_stream = true;
     bool packed = false;      // pack_kernel already ran for the batch in flight
@@ -217,7 +219,10 @@ struct ScopedTiming {
 // Enqueue the whole pipeline for `n` frames at `d_frames` on the slot's stream.
 int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack);
 
-int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bool pack)
+enum TailMode { TAIL_SIZES = 0, TAIL_PACK = 1, TAIL_SINGLE = 2 };
+int enqueue_single_tail(h2j_encoder *e, Slot &sl);
+
+int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, int tail)
 {
     const FrameLayout &L = sl.L;
     cudaStream_t st = sl.stream;
@@ -276,7 +281,24 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, bo
     CU(e, cudaGetLastError());
     // sizes/status (and, for host consumers, the packed payload) are produced inside the same enqueue so that
     // collecting a batch costs no further kernel launches
-    return enqueue_pack_and_sizes(e, sl, pack);
+    if (tail == TAIL_SINGLE) return enqueue_single_tail(e, sl);
+    return enqueue_pack_and_sizes(e, sl, tail == TAIL_PACK);
+}
+
+// h2j_encode_frame: no offsets kernel, no packing -- the frame's status / size fields and the first spec_bytes of its JPEG
+// come back with two copies enqueued behind the kernels, so one synchronisation ends the call when the guess holds.
+constexpr size_t kTabTailOff = offsetof(FrameTab, status);
+constexpr size_t kTabTailBytes = sizeof(FrameTab) - kTabTailOff;
+int enqueue_single_tail(h2j_encoder *e, Slot &sl)
+{
+    cudaStream_t st = sl.stream;
+    sl.packed = false;
+    sl.chain = false;
+    CU(e, cudaMemcpyAsync(sl.h_tail, reinterpret_cast<const unsigned char *>(sl.d_tabs) + kTabTailOff, kTabTailBytes, cudaMemcpyDeviceToHost, st));
+    const size_t spec = std::min(std::min(sl.spec_bytes, e->out_cap), sl.h_stage_bytes);
+    CU(e, cudaMemcpyAsync(sl.h_stage, sl.d_out, spec, cudaMemcpyDeviceToHost, st));
+    CU(e, cudaEventRecord(sl.ev_done, st));
+    return H2J_OK;
 }
 
 int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
@@ -317,6 +339,7 @@ void free_slot(Slot &sl)
     if (sl.h_status) cudaFreeHost(sl.h_status);
     if (sl.h_sizes) cudaFreeHost(sl.h_sizes);
     if (sl.h_stage) cudaFreeHost(sl.h_stage);
+    if (sl.h_tail) cudaFreeHost(sl.h_tail);
     for (auto &ev : sl.events) cudaEventDestroy(ev);
     if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
@@ -480,6 +503,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         const size_t padded = (size_t)mcu_w * 16 * mcu_h * 16 * 3 / 2;
         s0.h_stage_bytes = std::max(std::max(e->frame_bytes_cap, e->out_cap), padded);
         CUB(cudaHostAlloc(&s0.h_stage, s0.h_stage_bytes, cudaHostAllocDefault));
+        CUB(cudaHostAlloc(&s0.h_tail, 64, cudaHostAllocDefault));
     }
 #undef CUB
     *out = e;
@@ -499,7 +523,7 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     if (rc) return rc;
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
-    rc = launch_pipeline(e, sl, d_frames, n, false);
+    rc = launch_pipeline(e, sl, d_frames, n, TAIL_SIZES);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -532,7 +556,7 @@ int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, si
         d_frames, (long long)frame_stride, pitch, (long long)uv_offset, sl.d_frames, sl.L, src_aligned16);
     e->launches++;
     CU(e, cudaGetLastError());
-    rc = launch_pipeline(e, sl, sl.d_frames, n, false);
+    rc = launch_pipeline(e, sl, sl.d_frames, n, TAIL_SIZES);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -557,7 +581,7 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     if (frame_stride == dstride) CU(e, cudaMemcpyAsync(sl.d_frames, frames, dstride * (n - 1) + fb, cudaMemcpyHostToDevice, sl.stream));
     else CU(e, cudaMemcpy2DAsync(sl.d_frames, dstride, frames, frame_stride, fb, n, cudaMemcpyHostToDevice, sl.stream));
-    rc = launch_pipeline(e, sl, sl.d_frames, n, true);
+    rc = launch_pipeline(e, sl, sl.d_frames, n, TAIL_PACK);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -649,27 +673,55 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
-    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels)
-    uint8_t *p = sl.h_stage;
-    for (int r = 0; r < height; r++) memcpy(p + (size_t)r * width, planes[0] + (size_t)r * strides[0], width);
-    p += (size_t)width * height;
-    for (int pl = 1; pl <= 2; pl++) {
-        for (int r = 0; r < fch; r++) memcpy(p + (size_t)r * fcw, planes[pl] + (size_t)r * strides[pl], fcw);
-        p += (size_t)fcw * fch;
-    }
+    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels), uploaded in pieces of
+    // ~512 KiB so that the DMA of one piece runs under the memcpy of the next
+    CU(e, cudaSetDevice(e->s.device));
     const size_t fb = tight_frame_bytes(width, height);
-    int rc = h2j_submit_host(e, 0, sl.h_stage, align_up(fb, 256), 1, width, height);
+    const size_t dstride = align_up(fb, 256);
+    if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
+    int rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
     if (rc) return rc;
-    size_t offs[2] = {0, 0};
+    sl.n = 1;
+    CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
+    {
+        size_t off = 0;
+        auto plane = [&](const uint8_t *src, int stride, int pw, int ph) -> int {
+            const int rows_per_piece = std::max(1, (512 * 1024) / pw);
+            for (int r0 = 0; r0 < ph; r0 += rows_per_piece) {
+                const int r1 = std::min(ph, r0 + rows_per_piece);
+                uint8_t *dst = sl.h_stage + off + (size_t)r0 * pw;
+                if (stride == pw) memcpy(dst, src + (size_t)r0 * stride, (size_t)(r1 - r0) * pw);
+                else
+                    for (int r = r0; r < r1; r++) memcpy(dst + (size_t)(r - r0) * pw, src + (size_t)r * stride, pw);
+                CU(e, cudaMemcpyAsync(sl.d_frames + off + (size_t)r0 * pw, dst, (size_t)(r1 - r0) * pw, cudaMemcpyHostToDevice, sl.stream));
+            }
+            off += (size_t)pw * ph;
+            return H2J_OK;
+        };
+        if ((rc = plane(planes[0], strides[0], width, height))) return rc;
+        if ((rc = plane(planes[1], strides[1], fcw, fch))) return rc;
+        if ((rc = plane(planes[2], strides[2], fcw, fch))) return rc;
+    }
+    rc = launch_pipeline(e, sl, sl.d_frames, 1, TAIL_SINGLE);
+    if (rc) return rc;
+    CU(e, cudaStreamSynchronize(sl.stream));
     int st = 0;
-    // JPEG comes back through the pinned staging buffer when it fits, so the D2H copy is a true async DMA
-    uint8_t *dst = (e->out_cap <= sl.h_stage_bytes) ? sl.h_stage : out;
-    const size_t dcap = (dst == out) ? out_capacity : sl.h_stage_bytes;
-    rc = h2j_collect(e, 0, dst, dcap, offs, &st);
-    if (rc) return rc;
-    *out_size = offs[1];
-    if (offs[1] > out_capacity) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "JPEG is %zu bytes, caller gave %zu", offs[1], out_capacity);
-    if (dst != out) memcpy(out, dst, offs[1]);
+    long long jpeg_bytes = 0;
+    memcpy(&st, sl.h_tail + (offsetof(FrameTab, status) - kTabTailOff), sizeof st);
+    memcpy(&jpeg_bytes, sl.h_tail + (offsetof(FrameTab, jpeg_bytes) - kTabTailOff), sizeof jpeg_bytes);
+    if (st != 0) return fail(e, st, "the frame failed: %s", h2j_status_string(st));
+    if (jpeg_bytes < 0 || (size_t)jpeg_bytes > e->out_cap) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "JPEG of %lld bytes exceeds max_jpeg_bytes", jpeg_bytes);
+    const size_t n_out = (size_t)jpeg_bytes;
+    *out_size = n_out;
+    if (n_out > out_capacity) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "JPEG is %zu bytes, caller gave %zu", n_out, out_capacity);
+    const size_t spec = std::min(std::min(sl.spec_bytes, e->out_cap), sl.h_stage_bytes);
+    const size_t have = std::min(n_out, spec);
+    memcpy(out, sl.h_stage, have);
+    if (n_out > have) {  // the guess was short: the rest straight into the caller's buffer
+        CU(e, cudaMemcpy(out + have, sl.d_out + have, n_out - have, cudaMemcpyDeviceToHost));
+    }
+    // next guess: a quarter above this frame, in 64 KiB steps (consecutive frames of a stream are alike)
+    sl.spec_bytes = std::max<size_t>(64 * 1024, align_up(n_out + n_out / 4, 64 * 1024));
     return H2J_OK;
 }
 
