@@ -195,6 +195,11 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// ask for a range of global memory to be brought into L2 (TMA engine, fire and forget: no shared memory, nothing to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // the issuing thread's bulk stores have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // ... and have completed altogether

@@ -51,6 +51,10 @@ constexpr int kWarpWinStride = kWarpWinWords + 4;            // spare words for 
 constexpr int kSlotWords = 8;                                // private slot of a block: 256 bits
 constexpr int kSlotBits = kSlotWords * 32;
 constexpr int kSlotStride = kSlotWords + 1;                  // odd stride: the lanes' word i never share a bank
+#ifndef H2J_ENT_PREFETCH_DISTANCE
+#define H2J_ENT_PREFETCH_DISTANCE 1024
+#endif
+constexpr int kEntPrefetchDistance = H2J_ENT_PREFETCH_DISTANCE;  // K4a: CTAs ahead whose image is requested into L2 (148 SMs x 10 CTAs are resident)
 constexpr int kPlaceGroupUnits = 256;                        // K4b: units per CTA, one per thread
 constexpr int kPlaceThreads = 256;
 #ifndef H2J_PLACE_BATCH
@@ -211,6 +215,15 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
         bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
+        // CTAs are dispatched in linear order, so this one asks for the image of a CTA that starts a fraction of a CTA
+        // lifetime (~4 us) from now to be brought into L2; that CTA's bulk copy then finds it there.  Worth 1.3 % of the
+        // kernel (any distance from 384 to 2048 CTAs measures the same, 4096 is 12 % slower): most of the wait behind
+        // the mbarrier is not DRAM latency.
+        const long long lin = (long long)f * gridDim.x + tile + kEntPrefetchDistance;
+        if (lin < (long long)gridDim.x * gridDim.y) {
+            const long long f2 = lin / gridDim.x, t2 = lin - f2 * gridDim.x;
+            bulk_prefetch_l2(images + (f2 * images_cap + t2 * kEntFdctTiles) * kTileImageWords, kEntFdctTiles * kTileImageBytes);
+        }
     }
     for (int i = tid; i < kEntWarps * kWarpWinStride; i += kEntThreads) s_win_all[i] = 0;  // while the copies are on their way
     __syncthreads();  // barrier initialised, windows cleared (clearing only the words a unit needs, once its length is
