@@ -29,6 +29,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
     uint8_t *d_frames = nullptr;  // staging for host submits
+    uint8_t *d_pitched = nullptr; // copies of frames with unaligned rows at a 16-byte pitch (allocated on first need)
     uint32_t *d_images = nullptr;  // [max_batch][images_cap] tile images (h2j_common.cuh)
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
@@ -186,6 +187,49 @@ int make_layout(h2j_encoder *e, const uint8_t *base, size_t frame_stride, int w,
     return H2J_OK;
 }
 
+// Rows that do not start on 8-byte boundaries would send every block of K1 / K2 down the bytewise path: such batches are
+// copied once to a 16-byte row pitch (repitch_kernel, ~1 us per 1080p frame) and the pipeline reads the copy.
+// On return sl.L describes what the pipeline reads and *pipe_src is where it reads it.
+size_t pitched_frame_bytes(int w, int h)
+{
+    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
+    return align_up(align_up((size_t)w, 16) * h + 2 * align_up((size_t)fcw, 16) * fch, 256);
+}
+
+int prepare_input(h2j_encoder *e, Slot &sl, const uint8_t *d_src, size_t src_stride, int n, int w, int h, const uint8_t **pipe_src)
+{
+    int rc = make_layout(e, d_src, src_stride, w, h, &sl.L);
+    if (rc) return rc;
+    *pipe_src = d_src;
+    static const bool no_repitch = getenv("H2J_NO_REPITCH") != nullptr;  // measurement knob
+    if (sl.L.aligned8 || no_repitch) return H2J_OK;
+    if (!sl.d_pitched) {
+        const size_t bytes = pitched_frame_bytes(e->s.max_width, e->s.max_height) * (size_t)e->s.max_batch;
+        if (cudaMalloc(&sl.d_pitched, bytes) != cudaSuccess) {  // no room for the copy: the bytewise path still works
+            cudaGetLastError();
+            sl.d_pitched = nullptr;
+            return H2J_OK;
+        }
+    }
+    const FrameLayout T = sl.L;
+    FrameLayout P = T;
+    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
+    P.y_pitch = (int)align_up((size_t)w, 16);
+    P.c_pitch = (int)align_up((size_t)fcw, 16);
+    P.u_off = (long long)P.y_pitch * h;
+    P.v_off = P.u_off + (long long)P.c_pitch * fch;
+    P.frame_stride = (long long)pitched_frame_bytes(w, h);
+    P.aligned8 = 1;
+    P.aligned16 = 1;
+    const uint8_t *src_end = d_src + (size_t)(n - 1) * src_stride + tight_frame_bytes(w, h);
+    repitch_kernel<<<dim3((w + 128 * 16 - 1) / (128 * 16), (h + 2 * fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(d_src, T, sl.d_pitched, P, d_src, src_end);
+    e->launches++;
+    CU(e, cudaGetLastError());
+    sl.L = P;
+    *pipe_src = sl.d_pitched;
+    return H2J_OK;
+}
+
 struct ScopedTiming {
     Slot &sl;
     bool on;
@@ -333,7 +377,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_images); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
+    cudaFree(sl.d_frames); cudaFree(sl.d_pitched); cudaFree(sl.d_images); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -519,11 +563,12 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
     if (frame_stride < tight_frame_bytes(width, height)) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
     CU(e, cudaSetDevice(e->s.device));
-    rc = make_layout(e, d_frames, frame_stride, width, height, &sl.L);
-    if (rc) return rc;
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
-    rc = launch_pipeline(e, sl, d_frames, n, TAIL_SIZES);
+    const uint8_t *pipe_src = nullptr;
+    rc = prepare_input(e, sl, d_frames, frame_stride, n, width, height, &pipe_src);
+    if (rc) return rc;
+    rc = launch_pipeline(e, sl, pipe_src, n, TAIL_SIZES);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -552,11 +597,14 @@ int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, si
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     const int src_aligned16 = ((uintptr_t)d_frames % 16) == 0 && (frame_stride % 16) == 0 && (pitch % 16) == 0 ? 1 : 0;
     const int row_bytes = width > 2 * fcw ? width : 2 * fcw;
-    nv12_to_i420_kernel<<<dim3((row_bytes + 128 * 16 - 1) / (128 * 16), height + fch, n), 128, 0, sl.stream>>>(
+    nv12_to_i420_kernel<<<dim3((row_bytes + 128 * 16 - 1) / (128 * 16), (height + fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(
         d_frames, (long long)frame_stride, pitch, (long long)uv_offset, sl.d_frames, sl.L, src_aligned16);
     e->launches++;
     CU(e, cudaGetLastError());
-    rc = launch_pipeline(e, sl, sl.d_frames, n, TAIL_SIZES);
+    const uint8_t *pipe_src = nullptr;
+    rc = prepare_input(e, sl, sl.d_frames, dstride, n, width, height, &pipe_src);  // (odd widths: once more, to a 16-byte pitch)
+    if (rc) return rc;
+    rc = launch_pipeline(e, sl, pipe_src, n, TAIL_SIZES);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -581,7 +629,10 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     if (frame_stride == dstride) CU(e, cudaMemcpyAsync(sl.d_frames, frames, dstride * (n - 1) + fb, cudaMemcpyHostToDevice, sl.stream));
     else CU(e, cudaMemcpy2DAsync(sl.d_frames, dstride, frames, frame_stride, fb, n, cudaMemcpyHostToDevice, sl.stream));
-    rc = launch_pipeline(e, sl, sl.d_frames, n, TAIL_PACK);
+    const uint8_t *pipe_src = nullptr;
+    rc = prepare_input(e, sl, sl.d_frames, dstride, n, width, height, &pipe_src);
+    if (rc) return rc;
+    rc = launch_pipeline(e, sl, pipe_src, n, TAIL_PACK);
     if (rc) return rc;
     sl.busy = true;
     return H2J_OK;
@@ -702,7 +753,10 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
         if ((rc = plane(planes[1], strides[1], fcw, fch))) return rc;
         if ((rc = plane(planes[2], strides[2], fcw, fch))) return rc;
     }
-    rc = launch_pipeline(e, sl, sl.d_frames, 1, TAIL_SINGLE);
+    const uint8_t *pipe_src = nullptr;
+    rc = prepare_input(e, sl, sl.d_frames, dstride, 1, width, height, &pipe_src);
+    if (rc) return rc;
+    rc = launch_pipeline(e, sl, pipe_src, 1, TAIL_SINGLE);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(sl.stream));
     int st = 0;

@@ -137,18 +137,21 @@ __global__ void __launch_bounds__(128) convert_pad_kernel(const uint8_t *__restr
 // ------------------------------------------------------------------------------------------------
 // NV12 (what hardware decoders produce: a luma plane and ONE plane of interleaved Cb/Cr pairs, both with a row pitch)
 // -> the tight I420 frames the pipeline reads.  grid (x, rows, frames): rows 0..h-1 copy luma, rows h..h+ch-1 split a
-// chroma row.  16 bytes per thread where pitch, base and width allow, bytes otherwise.
+// chroma row (kPlaneRowsPerCta rows per CTA: one row per CTA made 400 k CTAs of 120 busy threads for 256 frames).
+// 16 bytes per thread where pitch, base and width allow, bytes otherwise.
 // ------------------------------------------------------------------------------------------------
+constexpr int kPlaneRowsPerCta = 16;
 __global__ void __launch_bounds__(128) nv12_to_i420_kernel(const uint8_t *__restrict__ src, long long src_stride, int pitch, long long uv_off,
                                                            uint8_t *__restrict__ dst, FrameLayout L, int src_aligned16)
 {
-    const int f = blockIdx.z, row = blockIdx.y;
+    const int f = blockIdx.z;
     const uint8_t *S = src + (long long)f * src_stride;
     uint8_t *D = dst + (long long)f * L.frame_stride;
     const int fch = (L.h + 1) >> 1;
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    for (int row = blockIdx.y * kPlaneRowsPerCta; row < min((int)(blockIdx.y + 1) * kPlaneRowsPerCta, L.h + fch); row++)
     if (row < L.h) {
-        if (x0 >= L.w) return;
+        if (x0 >= L.w) continue;
         const uint8_t *s = S + (long long)row * pitch + x0;
         uint8_t *d = D + (long long)row * L.y_pitch + x0;
         if (src_aligned16 && L.aligned16 && x0 + 16 <= L.w) *reinterpret_cast<uint4 *>(d) = ldg128(s);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(128) nv12_to_i420_kernel(const uint8_t *__rest
             for (int i = 0; i < 16 && x0 + i < L.w; i++) d[i] = s[i];
     } else if (row < L.h + fch) {
         const int r = row - L.h;
-        if (x0 >= 2 * L.c_pitch) return;  // c_pitch = ceil(w / 2) pairs per row
+        if (x0 >= 2 * L.c_pitch) continue;  // c_pitch = ceil(w / 2) pairs per row
         const uint8_t *s = S + uv_off + (long long)r * pitch + x0;
         uint8_t *du = D + L.u_off + (long long)r * L.c_pitch + (x0 >> 1), *dv = D + L.v_off + (long long)r * L.c_pitch + (x0 >> 1);
         if (src_aligned16 && (uv_off & 15) == 0 && L.aligned8 && x0 + 16 <= 2 * L.c_pitch) {
@@ -171,6 +174,44 @@ __global__ void __launch_bounds__(128) nv12_to_i420_kernel(const uint8_t *__rest
                 dv[i] = s[2 * i + 1];
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tight I420 frames whose rows do not start on 8-byte boundaries (odd widths such as 1918, or an unaligned base) ->
+// the same planes at a 16-byte row pitch, so that K1 and K2 take their vector-load paths (every block but the ones cut
+// by the right edge) instead of 64 byte loads per block.  grid (x, h + 2 * ceil(h/2), frames); a thread produces 16
+// output bytes from five aligned source words and four funnel shifts.  The padding bytes of a row are never read by
+// the pipeline (edges are replicated from the last real sample).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) repitch_kernel(const uint8_t *__restrict__ src, FrameLayout T,  // tight layout of the source
+                                                      uint8_t *__restrict__ dst, FrameLayout P,        // pitched layout of the copy
+                                                      const uint8_t *src_begin, const uint8_t *src_end)
+{
+    const int f = blockIdx.z;
+    const int fch = (T.h + 1) >> 1;
+    for (int row = blockIdx.y * kPlaneRowsPerCta; row < min((int)(blockIdx.y + 1) * kPlaneRowsPerCta, T.h + 2 * fch); row++) {
+    int pw, r;
+    long long so, dof;
+    int spitch, dpitch;
+    if (row < T.h) { pw = T.w; r = row; so = 0; dof = 0; spitch = T.y_pitch; dpitch = P.y_pitch; }
+    else if (row < T.h + fch) { pw = T.c_pitch; r = row - T.h; so = T.u_off; dof = P.u_off; spitch = T.c_pitch; dpitch = P.c_pitch; }
+    else { pw = T.c_pitch; r = row - T.h - fch; so = T.v_off; dof = P.v_off; spitch = T.c_pitch; dpitch = P.c_pitch; }
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x0 >= pw) continue;
+    const uint8_t *s = src + (long long)f * T.frame_stride + so + (long long)r * spitch + x0;
+    uint8_t *d = dst + (long long)f * P.frame_stride + dof + (long long)r * dpitch + x0;  // 16-byte aligned, x0 + 16 <= dpitch
+    const unsigned a = (unsigned)((uintptr_t)s & 3u);
+    const uint8_t *s4 = s - a;
+    if (s4 >= src_begin && s4 + 20 <= src_end) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(s4);
+        const unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = a ? __ldg(q + 4) : 0u;
+        const unsigned sh = a * 8;
+        *reinterpret_cast<uint4 *>(d) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                                   __funnelshift_r(w3, w4, sh));
+    } else {
+        for (int i = 0; i < 16 && x0 + i < pw; i++) d[i] = s[i];
+    }
     }
 }
 
