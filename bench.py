@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's ffmpeg-mjpeg CPU path on the host cores
 
-A step is one pass of the hot path over one batch of `--frames` distinct frames (default 512 x 1080p = 1.6 GB
+A step is one pass of the hot path over one batch of `--frames` distinct frames (default 2048 x 1080p = 6.4 GB
 of input, larger than the 126 MB L2, so nothing is served from cache between steps).
   value : frames/s, whole job, inputs already resident in HBM (h2j_submit_device), CUDA-event timed.
   e2e   : frames/s through the public C ABI with HOST buffers: pinned I420 frames in (H2D every step), JPEG
@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--frames", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=2048, help="frames per step per GPU")
     ap.add_argument("--sub-batch", type=int, default=0, help="frames per submitted batch of the device-resident pass (0 = --frames)")
     ap.add_argument("--slots", type=int, default=1, help="batches in flight (streams) of the device-resident pass; 1 keeps the per-kernel "
                                                          "CUDA-event brackets free of other streams' kernels")
