@@ -1,0 +1,57 @@
+"""CPU suite: the parts of bench.py that do not need a GPU -- the JSON line goes to the saved stdout only, the NUMA binding
+is a no-op when the topology cannot be read, the clock sampler degrades to "no samples" instead of failing, and the
+reference arm prints the contract's keys."""
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_numa_local_is_a_no_op_without_topology():
+    import bench
+
+    before = os.sched_getaffinity(0)
+    n = bench.NumaLocal(0)
+    with n:
+        inside = os.sched_getaffinity(0)
+    assert os.sched_getaffinity(0) == before
+    assert n.node is not None or inside == before
+
+
+def test_clock_sampler_degrades():
+    import bench
+
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_emit_line_is_one_json_line():
+    import bench
+
+    buf = io.StringIO()
+    old = bench._json_out
+    bench._json_out = buf
+    try:
+        bench.emit_line({"metric": bench.METRIC, "value": 1.0})
+    finally:
+        bench._json_out = old
+    lines = buf.getvalue().splitlines()
+    assert len(lines) == 1 and json.loads(lines[0])["value"] == 1.0
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-frames", "4",
+                        "--width", "320", "--height", "240"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
