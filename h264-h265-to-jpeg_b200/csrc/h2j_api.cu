@@ -196,6 +196,21 @@ size_t pitched_frame_bytes(int w, int h)
     return align_up(align_up((size_t)w, 16) * h + 2 * align_up((size_t)fcw, 16) * fch, 256);
 }
 
+// the same frame at a 16-byte row pitch in a 16-byte aligned buffer
+FrameLayout pitched_layout(const FrameLayout &T)
+{
+    FrameLayout P = T;
+    const int fcw = (T.w + 1) >> 1, fch = (T.h + 1) >> 1;
+    P.y_pitch = (int)align_up((size_t)T.w, 16);
+    P.c_pitch = (int)align_up((size_t)fcw, 16);
+    P.u_off = (long long)P.y_pitch * T.h;
+    P.v_off = P.u_off + (long long)P.c_pitch * fch;
+    P.frame_stride = (long long)pitched_frame_bytes(T.w, T.h);
+    P.aligned8 = 1;
+    P.aligned16 = 1;
+    return P;
+}
+
 int prepare_input(h2j_encoder *e, Slot &sl, const uint8_t *d_src, size_t src_stride, int n, int w, int h, const uint8_t **pipe_src)
 {
     int rc = make_layout(e, d_src, src_stride, w, h, &sl.L);
@@ -212,15 +227,8 @@ int prepare_input(h2j_encoder *e, Slot &sl, const uint8_t *d_src, size_t src_str
         }
     }
     const FrameLayout T = sl.L;
-    FrameLayout P = T;
-    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
-    P.y_pitch = (int)align_up((size_t)w, 16);
-    P.c_pitch = (int)align_up((size_t)fcw, 16);
-    P.u_off = (long long)P.y_pitch * h;
-    P.v_off = P.u_off + (long long)P.c_pitch * fch;
-    P.frame_stride = (long long)pitched_frame_bytes(w, h);
-    P.aligned8 = 1;
-    P.aligned16 = 1;
+    const FrameLayout P = pitched_layout(T);
+    const int fch = (h + 1) >> 1;
     const uint8_t *src_end = d_src + (size_t)(n - 1) * src_stride + tight_frame_bytes(w, h);
     repitch_kernel<<<dim3((w + 128 * 16 - 1) / (128 * 16), (h + 2 * fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(d_src, T, sl.d_pitched, P, d_src, src_end);
     e->launches++;
@@ -493,7 +501,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     // at most one word of slack each)
     e->stage_cap_words = (long long)e->units_cap * kWarpWinWords + e->scan_cap_words + e->units_cap;
     e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
-    e->frame_bytes_cap = align_up(tight_frame_bytes(s->max_width, s->max_height), 256);
+    e->frame_bytes_cap = std::max(align_up(tight_frame_bytes(s->max_width, s->max_height), 256), pitched_frame_bytes(s->max_width, s->max_height));
 
     // constant tables
     {
@@ -732,31 +740,30 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
     int rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
     if (rc) return rc;
+    // rows that would not start on 8-byte boundaries (odd widths) are staged at a 16-byte pitch right here: the rows are
+    // copied one by one anyway, and the kernels keep their vector loads without a second pass over the frame
+    if (!sl.L.aligned8) sl.L = pitched_layout(sl.L);
+    const FrameLayout &L = sl.L;
     sl.n = 1;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     {
-        size_t off = 0;
-        auto plane = [&](const uint8_t *src, int stride, int pw, int ph) -> int {
-            const int rows_per_piece = std::max(1, (512 * 1024) / pw);
+        auto plane = [&](const uint8_t *src, int stride, size_t off, int pw, int pitch, int ph) -> int {
+            const int rows_per_piece = std::max(1, (512 * 1024) / pitch);
             for (int r0 = 0; r0 < ph; r0 += rows_per_piece) {
                 const int r1 = std::min(ph, r0 + rows_per_piece);
-                uint8_t *dst = sl.h_stage + off + (size_t)r0 * pw;
-                if (stride == pw) memcpy(dst, src + (size_t)r0 * stride, (size_t)(r1 - r0) * pw);
+                uint8_t *dst = sl.h_stage + off + (size_t)r0 * pitch;
+                if (stride == pw && pitch == pw) memcpy(dst, src + (size_t)r0 * stride, (size_t)(r1 - r0) * pw);
                 else
-                    for (int r = r0; r < r1; r++) memcpy(dst + (size_t)(r - r0) * pw, src + (size_t)r * stride, pw);
-                CU(e, cudaMemcpyAsync(sl.d_frames + off + (size_t)r0 * pw, dst, (size_t)(r1 - r0) * pw, cudaMemcpyHostToDevice, sl.stream));
+                    for (int r = r0; r < r1; r++) memcpy(dst + (size_t)(r - r0) * pitch, src + (size_t)r * stride, pw);
+                CU(e, cudaMemcpyAsync(sl.d_frames + off + (size_t)r0 * pitch, dst, (size_t)(r1 - r0 - 1) * pitch + pw, cudaMemcpyHostToDevice, sl.stream));
             }
-            off += (size_t)pw * ph;
             return H2J_OK;
         };
-        if ((rc = plane(planes[0], strides[0], width, height))) return rc;
-        if ((rc = plane(planes[1], strides[1], fcw, fch))) return rc;
-        if ((rc = plane(planes[2], strides[2], fcw, fch))) return rc;
+        if ((rc = plane(planes[0], strides[0], 0, width, L.y_pitch, height))) return rc;
+        if ((rc = plane(planes[1], strides[1], (size_t)L.u_off, fcw, L.c_pitch, fch))) return rc;
+        if ((rc = plane(planes[2], strides[2], (size_t)L.v_off, fcw, L.c_pitch, fch))) return rc;
     }
-    const uint8_t *pipe_src = nullptr;
-    rc = prepare_input(e, sl, sl.d_frames, dstride, 1, width, height, &pipe_src);
-    if (rc) return rc;
-    rc = launch_pipeline(e, sl, pipe_src, 1, TAIL_SINGLE);
+    rc = launch_pipeline(e, sl, sl.d_frames, 1, TAIL_SINGLE);
     if (rc) return rc;
     CU(e, cudaStreamSynchronize(sl.stream));
     int st = 0;
