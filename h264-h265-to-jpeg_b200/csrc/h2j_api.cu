@@ -184,6 +184,7 @@ int make_layout(h2j_encoder *e, const uint8_t *base, size_t frame_stride, int w,
     L->aligned16 = ((uintptr_t)base % 16) == 0 && (frame_stride % 16) == 0 && (L->y_pitch % 16) == 0 ? 1 : 0;
     L->range_mode = e->s.range_mode;
     L->fixed_qscale = e->s.fixed_qscale;
+    L->nv12 = 0;
     return H2J_OK;
 }
 
@@ -297,8 +298,9 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
-        fdct_quant_kernel<<<dim3(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n), kFdctThreads, extra_smem, st>>>(
-            d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        const dim3 grid(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
+        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }
     {
@@ -515,7 +517,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMalloc(&e->d_comment, e->comment.size() + 1));
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
-    if (getenv("H2J_K2_EXTRA_SMEM")) CUB(cudaFuncSetAttribute(fdct_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (getenv("H2J_K2_EXTRA_SMEM")) CUB(cudaFuncSetAttribute(fdct_quant_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUB(cudaFuncSetAttribute(entropy_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
 
     const int B = s->max_batch;
@@ -603,6 +605,25 @@ int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, si
     if (rc) return rc;
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
+    // Rows on 8-byte boundaries (what decoders produce): the pipeline reads the NV12 frames where they are -- K1 only looks
+    // at luma, K2's chroma warps fetch the pairs and split them in registers.  Otherwise the pairs are split into the
+    // slot's I420 buffer first (one more pass over the frame).
+    static const bool force_prepass = getenv("H2J_NV12_PREPASS") != nullptr;  // measurement knob
+    if (!force_prepass && (uintptr_t)d_frames % 8 == 0 && frame_stride % 8 == 0 && pitch % 8 == 0 && uv_offset % 8 == 0) {
+        FrameLayout &L = sl.L;
+        L.y_pitch = pitch;
+        L.c_pitch = pitch;
+        L.u_off = (long long)uv_offset;
+        L.v_off = (long long)uv_offset;
+        L.frame_stride = (long long)frame_stride;
+        L.aligned8 = 1;
+        L.aligned16 = ((uintptr_t)d_frames % 16 == 0 && frame_stride % 16 == 0 && pitch % 16 == 0) ? 1 : 0;
+        L.nv12 = 1;
+        rc = launch_pipeline(e, sl, d_frames, n, TAIL_SIZES);
+        if (rc) return rc;
+        sl.busy = true;
+        return H2J_OK;
+    }
     const int src_aligned16 = ((uintptr_t)d_frames % 16) == 0 && (frame_stride % 16) == 0 && (pitch % 16) == 0 ? 1 : 0;
     const int row_bytes = width > 2 * fcw ? width : 2 * fcw;
     nv12_to_i420_kernel<<<dim3((row_bytes + 128 * 16 - 1) / (128 * 16), (height + fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(

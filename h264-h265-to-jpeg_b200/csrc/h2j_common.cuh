@@ -31,6 +31,7 @@ struct FrameLayout {
     int aligned16;     // ... 16-byte boundary -> 128-bit loads (mbvar)
     int range_mode;
     int fixed_qscale;
+    int nv12;          // chroma is ONE plane of interleaved Cb/Cr pairs at u_off, rows c_pitch apart (v_off unused)
 };
 
 // ---- coefficient store ("tile images") -----------------------------------------------------------

@@ -34,19 +34,25 @@ namespace h2j {
 // What a thread needs to know about the plane its block lives in: fixed for the whole kernel.
 struct PlaneRef {
     const uint8_t *P;
-    int pitch, pw, ph;   // row pitch in bytes, width / height the encoder reads (edges are replicated beyond)
-    int step;            // block spacing per MCU: 16 luma, 8 chroma
-    int xoff, yoff;      // block offset inside the MCU
+    int pitch, pw, ph;   // row pitch in bytes, width in BYTES / height in rows the encoder reads (edges are replicated beyond)
+    int step, xstep;     // block spacing per MCU in rows (16 luma, 8 chroma) and in bytes (the same, but 16 for NV12 chroma)
+    int xoff, yoff;      // block offset inside the MCU (bytes / rows)
     bool can_fast;       // rows start 8-byte aligned: 64-bit loads
 };
-__device__ __forceinline__ PlaneRef plane_ref(const uint8_t *base, const FrameLayout &L, int n)
+// NV12 (template parameter of the kernel): the chroma plane holds Cb/Cr PAIRS, so an MCU's two chroma blocks are the 16
+// bytes [16 mx, 16 mx + 16) of eight rows; the Cb lane fetches the first eight bytes of every row, the Cr lane (16 lanes
+// up) the other eight, and they trade halves before the transform (nv12_trade).
+template <bool NV12> __device__ __forceinline__ PlaneRef plane_ref(const uint8_t *base, const FrameLayout &L, int n)
 {
     PlaneRef r;
     if (n < 4) {
-        r.P = base; r.pitch = L.y_pitch; r.pw = L.w; r.ph = L.h; r.step = 16;
+        r.P = base; r.pitch = L.y_pitch; r.pw = L.w; r.ph = L.h; r.step = 16; r.xstep = 16;
         r.xoff = (n & 1) * 8; r.yoff = (n >> 1) * 8;
+    } else if (NV12) {
+        r.P = base + L.u_off; r.pitch = L.c_pitch; r.pw = 2 * L.cw; r.ph = L.ch; r.step = 8; r.xstep = 16;
+        r.xoff = (n - 4) * 8; r.yoff = 0;
     } else {
-        r.P = base + (n == 4 ? L.u_off : L.v_off); r.pitch = L.c_pitch; r.pw = L.cw; r.ph = L.ch; r.step = 8;
+        r.P = base + (n == 4 ? L.u_off : L.v_off); r.pitch = L.c_pitch; r.pw = L.cw; r.ph = L.ch; r.step = 8; r.xstep = 8;
         r.xoff = 0; r.yoff = 0;
     }
     r.can_fast = L.aligned8 != 0;
@@ -61,14 +67,14 @@ struct BlockPos {
     {
         m = m_;
         const int my = m_ / mcu_w, mx = m_ - my * mcu_w;  // m_ = -1: my = 0, mx = -1
-        bx = mx * R.step + R.xoff;
+        bx = mx * R.xstep + R.xoff;
         by = my * R.step + R.yoff;
     }
     __device__ __forceinline__ void advance(const PlaneRef &R, int mcu_w)
     {
-        const int row_w = mcu_w * R.step;  // bx = mx * step + xoff with xoff < step: bx >= row_w <=> mx >= mcu_w
+        const int row_w = mcu_w * R.xstep;  // bx = mx * xstep + xoff with xoff < xstep: bx >= row_w <=> mx >= mcu_w
         m += kTileMcus;
-        bx += kTileMcus * R.step;
+        bx += kTileMcus * R.xstep;
         while (bx >= row_w) { bx -= row_w; by += R.step; }
     }
 };
@@ -82,13 +88,24 @@ struct BlockFetch {
     uint2 rows[8];
     uint2 prow;          // lanes that help with a predecessor DC: one row of that block
 };
-__device__ __forceinline__ bool fetch_is_fast(const PlaneRef &R, int bx) { return R.can_fast && bx + 8 <= R.pw; }
+// C = the block is an NV12 chroma block: the vector path needs the MCU's whole 16 bytes inside the row (both lanes of a
+// Cb/Cr pair take the same path, they trade halves), and sample c of the block is byte 2 * (x + c) + component.
+template <bool C> __device__ __forceinline__ bool fetch_is_fast(const PlaneRef &R, int bx)
+{
+    return R.can_fast && (C ? bx - R.xoff + 16 : bx + 8) <= R.pw;
+}
+template <bool C> __device__ __forceinline__ int sample_at(const uint8_t *row, const PlaneRef &R, int bx, int c)
+{
+    if (C) return row[2 * min(((bx - R.xoff) >> 1) + c, (R.pw >> 1) - 1) + (R.xoff >> 3)];
+    return row[min(bx + c, R.pw - 1)];
+}
 
+template <bool C, bool CQ>
 __device__ __forceinline__ void fetch_issue(BlockFetch &F, const uint8_t *safe, const PlaneRef &R, const BlockPos &bp, bool valid,
                                             const PlaneRef &Q, const BlockPos &pp, bool phelp, int prow_idx)
 {
-    const bool pf = phelp && fetch_is_fast(Q, pp.bx);
-    const bool rf = valid && fetch_is_fast(R, bp.bx);
+    const bool pf = !CQ && phelp && fetch_is_fast<false>(Q, pp.bx);  // (NV12 chroma: the predecessor rows are read bytewise)
+    const bool rf = valid && fetch_is_fast<C>(R, bp.bx);
     const uint8_t *pq = pf ? Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch + pp.bx : safe;
     F.prow = ldg64(pq);
     if (!rf || bp.by + 8 <= R.ph) {  // interior: one address, then a pitch per row
@@ -105,6 +122,20 @@ __device__ __forceinline__ void fetch_issue(BlockFetch &F, const uint8_t *safe, 
     }
 }
 
+// NV12 chroma warp, all 32 lanes: every row arrives as four Cb/Cr pairs; the Cb lane keeps the four Cb samples and hands
+// the four Cr samples to the Cr lane of its MCU (16 lanes up), which hands back the Cb samples of ITS four pairs.
+__device__ __forceinline__ void nv12_trade(BlockFetch &F, bool cr_lane)
+{
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const unsigned cb4 = __byte_perm(F.rows[r].x, F.rows[r].y, 0x6420), cr4 = __byte_perm(F.rows[r].x, F.rows[r].y, 0x7531);
+        const unsigned keep = cr_lane ? cr4 : cb4;
+        const unsigned got = __shfl_xor_sync(0xffffffffu, cr_lane ? cb4 : cr4, 16);
+        F.rows[r] = cr_lane ? make_uint2(got, keep) : make_uint2(keep, got);  // Cb lane had pairs 0-3, Cr lane pairs 4-7
+    }
+}
+
+template <bool C>
 __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRef &R, const BlockPos &bp, const uint8_t *lut, int (&v)[64])
 {
 #pragma unroll
@@ -119,12 +150,12 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRe
         v[r * 8 + 6] = (int)__byte_perm(F.rows[r].y, 0u, 0x4442);
         v[r * 8 + 7] = (int)__byte_perm(F.rows[r].y, 0u, 0x4443);
     }
-    if (!fetch_is_fast(R, bp.bx)) {
+    if (!fetch_is_fast<C>(R, bp.bx)) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const uint8_t *row = R.P + (long long)min(bp.by + r, R.ph - 1) * R.pitch;
 #pragma unroll
-            for (int c = 0; c < 8; c++) v[r * 8 + c] = row[min(bp.bx + c, R.pw - 1)];
+            for (int c = 0; c < 8; c++) v[r * 8 + c] = sample_at<C>(row, R, bp.bx, c);
         }
     }
     if (lut) {
@@ -134,23 +165,25 @@ __device__ __forceinline__ void fetch_consume(const BlockFetch &F, const PlaneRe
 }
 
 // this lane's share (one pixel row) of the predecessor block's sample sum
+template <bool CQ>
 __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const PlaneRef &Q, const BlockPos &pp, bool phelp, int prow_idx,
                                                  const uint8_t *lut)
 {
     int s = (int)__dp4a(F.prow.y, 0x01010101u, __dp4a(F.prow.x, 0x01010101u, 0u));
     if (!phelp) return 0;
-    if (!fetch_is_fast(Q, pp.bx) || lut) {
+    if (CQ || !fetch_is_fast<false>(Q, pp.bx) || lut) {
         const uint8_t *row = Q.P + (long long)min(pp.by + prow_idx, Q.ph - 1) * Q.pitch;
         s = 0;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int p = row[min(pp.bx + c, Q.pw - 1)];
+            const int p = sample_at<CQ>(row, Q, pp.bx, c);
             s += lut ? lut[p] : p;
         }
     }
     return s;
 }
 
+template <bool NV12>
 __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
                                                                      FrameState *__restrict__ state,
                                                                      const FrameTab *__restrict__ tabs,
@@ -182,7 +215,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     // chroma -> Cb (lanes 0-7 help) and Cr (lanes 8-15 help) of the MCU in front of the tile (first tile only)
     const bool phelp_lane = luma ? lane < 8 : lane < 16;
     const int mcu_first = luma ? warp * 8 : 0;
-    const PlaneRef R = plane_ref(base, L, n), Q = plane_ref(base, L, luma ? 3 : 4 + (lane >> 3));
+    const PlaneRef R = plane_ref<NV12>(base, L, n), Q = plane_ref<NV12>(base, L, luma ? 3 : 4 + (lane >> 3));
+    const bool nvc = NV12 && !luma;  // this warp's blocks are NV12 chroma blocks (CTA-uniform)
 
     BlockFetch F;
     const uint8_t *safe = reinterpret_cast<const uint8_t *>(tabs);  // aligned, always readable: what skipped loads read
@@ -191,7 +225,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     pp.init(tile0 * kTileMcus + mcu_first - 1, Q, L.mcu_w);
     // lanes that add a row of the predecessor block: chroma only needs it for its first tile (then the DC is carried)
     auto phelp_at = [&](int tile) { return phelp_lane && pp.m >= 0 && pp.m < L.n_mcu && (luma || tile == tile0); };
-    fetch_issue(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
+    if (nvc) fetch_issue<true, true>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
+    else fetch_issue<false, false>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile0), lane & 7);
 
     // ---- the frame's quantiser (set up once per frame by K1's last CTA), cleared statistics ----
     {
@@ -217,7 +252,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         __syncwarp();
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
-        int psum = fetch_pred_rowsum(F, Q, pp, phelp_at(tile), lane & 7, lut);
+        int psum = nvc ? fetch_pred_rowsum<true>(F, Q, pp, phelp_at(tile), lane & 7, lut) : fetch_pred_rowsum<false>(F, Q, pp, phelp_at(tile), lane & 7, lut);
+        if (nvc) nv12_trade(F, lane >= 16);  // (all 32 lanes, outside `valid`: the lanes of a pair share their MCU)
         psum += __shfl_xor_sync(0xffffffffu, psum, 1);
         psum += __shfl_xor_sync(0xffffffffu, psum, 2);
         psum += __shfl_xor_sync(0xffffffffu, psum, 4);
@@ -234,7 +270,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         uint32_t *rec = img + lane * kBlkWords;  // the lane order of every warp is its record order
         if (valid) {
             int v[64];
-            fetch_consume(F, R, bp, lut, v);
+            if (nvc) fetch_consume<true>(F, R, bp, lut, v);
+            else fetch_consume<false>(F, R, bp, lut, v);
             fdct_8x8(v);
             dc = quant_dc(v[0]);
             // quantise without the final >> 16: the level is the upper half of the 32-bit product, so two of them
@@ -263,7 +300,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         if (tile + 1 < tile_end) {
             bp.advance(R, L.mcu_w);
             pp.advance(Q, L.mcu_w);
-            fetch_issue(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
+            if (nvc) fetch_issue<true, true>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
+            else fetch_issue<false, false>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----

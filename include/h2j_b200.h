@@ -108,8 +108,9 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
                       int height);
 /* h2j_submit_device_nv12: the batch is NV12 in device memory, as hardware decoders (NVDEC) leave it: per frame a luma
  * plane of `height` rows and, `uv_offset` bytes behind the frame's start, a plane of ceil(height/2) rows of interleaved
- * Cb/Cr pairs; both planes have rows `pitch` bytes apart, frames are `frame_stride` bytes apart.  The pairs are split
- * into the slot's own I420 frame buffer by one extra kernel and the batch proceeds as in h2j_submit_device; the JPEGs are
+ * Cb/Cr pairs; both planes have rows `pitch` bytes apart, frames are `frame_stride` bytes apart.  With the pointer, the
+ * stride, the pitch and uv_offset multiples of 8 the frames are read where they are (the chroma pairs are split in
+ * registers); otherwise the pairs are first split into the slot's own I420 frame buffer by one extra kernel.  The JPEGs are
  * the ones the reference writes for the equivalent yuv420p frame (the reference itself has no NV12 input: its decoder is
  * libavcodec's software decoder, src/Decoder.cpp:183, :324-342).  Collect with h2j_collect / h2j_collect_device. */
 int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t frame_stride, int pitch,

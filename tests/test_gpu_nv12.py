@@ -28,6 +28,9 @@ def to_nv12(y, u, v, pitch, uv_rows_offset):
         (322, 242, 16, 0, "noise"),
         (17, 9, 1, 0, "noise"),             # odd width and height: ceil(w/2) pairs, ceil(h/2) chroma rows
         (64, 48, 64, 3, "const"),
+        (330, 241, 8, 1, "noise"),          # read in place: right edge cuts an MCU's pairs, odd height (ch = h >> 1 rows are read)
+        (1280, 720, 128, 0, "textured"),    # read in place, tiles wrap MCU rows
+        (48, 16, 8, 0, "noise"),            # a single MCU row, three MCUs: less than one tile
     ],
 )
 def test_nv12_matches_planar(orc, w, h, pitch_align, extra_rows, kind):
@@ -62,6 +65,24 @@ def test_nv12_matches_planar(orc, w, h, pitch_align, extra_rows, kind):
         e.submit_device_nv12(0, d2.data_ptr() + 1, stride, pitch, uv_off, n, w, h)
         res2 = e.collect(0)
         assert res2.jpegs == res.jpegs
+
+
+def test_nv12_in_place_with_range_conversion_and_fixed_qscale(orc):
+    """The in-place path through the limited->full LUT (bytewise predecessor rows, LUT on traded samples) and at a fixed
+    quantiser."""
+    import torch
+
+    import h2j_b200
+
+    w, h, pitch = 322, 242, 384
+    y, u, v = orc.synth_planes(w, h, "textured", seed=77)
+    fr = to_nv12(y, u, v, pitch, pitch * h)
+    d = torch.from_numpy(fr).cuda()
+    for kw, okw in (({"range_mode": 1}, {"range_mode": 1}), ({"fixed_qscale": 3}, {"fixed_qscale": 3})):
+        with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, **kw) as e:
+            e.submit_device_nv12(0, d.data_ptr(), len(fr), pitch, pitch * h, 1, w, h)
+            got = e.collect(0).jpegs[0]
+        assert got == orc.oracle_encode(y, u, v, **okw)[0], kw
 
 
 def test_nv12_argument_checks(orc):
