@@ -22,6 +22,14 @@ def run(args):
     return subprocess.run(["ncu"] + args, check=True, capture_output=True, text=True).stdout
 
 
+def kname(full):
+    """'void h2j::fdct_quant_kernel<(bool)0>(const unsigned char *, ...)' -> 'fdct_quant_kernel'"""
+    n = full.split("(")[0].split("<")[0].strip()
+    if n.startswith("void "):
+        n = n[5:]
+    return n.split("::")[-1]
+
+
 def main(rep, out):
     rows = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "raw", "--csv"]))))
     head, units, body = rows[0], rows[1], rows[2:]
@@ -30,7 +38,7 @@ def main(rep, out):
         w = csv.writer(f)
         w.writerow(["id", "kernel"] + [f"{c} [{units[head.index(c)]}]" for c in cols])
         for r in body:
-            w.writerow([r[head.index("ID")], r[head.index("Kernel Name")].split("(")[0]] + [r[head.index(c)] for c in cols])
+            w.writerow([r[head.index("ID")], kname(r[head.index("Kernel Name")])] + [r[head.index(c)] for c in cols])
     rows = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "details", "--csv"]))))
     head = rows[0]
     ki, idi, si, mi, ui, vi = (head.index(n) for n in ("Kernel Name", "ID", "Section Name", "Metric Name", "Metric Unit", "Metric Value"))
@@ -39,7 +47,7 @@ def main(rep, out):
         for r in rows[1:]:
             if r[si] not in SECTIONS or not r[mi]:
                 continue
-            key = (r[idi], r[ki].split("(")[0])
+            key = (r[idi], kname(r[ki]))
             if key != last:
                 f.write(f"\n==== launch {key[0]}: {key[1]}\n")
                 last = key
