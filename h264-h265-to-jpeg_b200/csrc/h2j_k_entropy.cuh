@@ -153,28 +153,38 @@ __device__ __forceinline__ unsigned walk_block(const int16_t *cb, unsigned mask_
     }
     int prev = 0;
     const uint32_t zrl = hac[0xf0];
+    // one coded level: zero-run escapes, then (run, size) code + mantissa
+    auto code_one = [&](int run, int val, int nb, uint32_t e) {
+        if (run >= 16) {
+            if (EMIT) {
+                for (int z = run >> 4; z > 0; z--) sink->put(zrl >> 5, zrl & 31);
+            } else total += (unsigned)(run >> 4) * (zrl & 31);
+        }
+        const int sz = e & 31;
+        if (EMIT) {
+            const unsigned mant = (unsigned)(val < 0 ? val - 1 : val) & ((1u << nb) - 1u);
+            sink->put(((e >> 5) << nb) | mant, sz + nb);
+        } else total += sz + nb;
+    };
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         unsigned mm = half ? mask_hi : mask_lo;
+        // two positions per trip: their position -> level -> size -> code look-ups are independent and overlap; only the
+        // emission is in order (the second one is predicated off when the lane has run out)
         while (mm) {
-            const int bp = __ffs((int)mm) - 1, k = half * 32 + bp;
-            mm &= mm - 1;
-            int run = k - prev - 1;
-            prev = k;
-            const int val = (int)cb[2 * bp + half];
-            const int nb = mag_bits(val);
-            if (run >= 16) {
-                if (EMIT) {
-                    for (int z = run >> 4; z > 0; z--) sink->put(zrl >> 5, zrl & 31);
-                } else total += (unsigned)(run >> 4) * (zrl & 31);
-                run &= 15;
-            }
-            const uint32_t e = hac[(run << 4) | nb];
-            const int sz = e & 31;
-            if (EMIT) {
-                const unsigned mant = (unsigned)(val < 0 ? val - 1 : val) & ((1u << nb) - 1u);
-                sink->put(((e >> 5) << nb) | mant, sz + nb);
-            } else total += sz + nb;
+            const unsigned b0 = mm & (0u - mm);
+            mm ^= b0;
+            const unsigned b1 = mm & (0u - mm);
+            mm ^= b1;
+            const int p0 = 31 - __clz(b0), p1 = b1 ? 31 - __clz(b1) : p0;
+            const int k0 = half * 32 + p0, k1 = half * 32 + p1;
+            const int val0 = (int)cb[2 * p0 + half], val1 = (int)cb[2 * p1 + half];
+            const int nb0 = mag_bits(val0), nb1 = mag_bits(val1);
+            const int run0 = k0 - prev - 1, run1 = k1 - k0 - 1;
+            const uint32_t e0 = hac[((run0 & 15) << 4) | nb0], e1 = hac[((run1 & 15) << 4) | nb1];
+            code_one(run0, val0, nb0, e0);
+            if (b1) code_one(run1, val1, nb1, e1);
+            prev = k1;
         }
     }
     if (prev < 63) {

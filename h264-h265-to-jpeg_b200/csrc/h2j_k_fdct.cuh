@@ -25,6 +25,10 @@
 #pragma once
 #include "h2j_common.cuh"
 
+#ifndef H2J_K2_WALK
+#define H2J_K2_WALK 2  // positions the statistics walk takes per trip from the low end (0: the two-ended walk).  K2 per 2048 frames:
+                      // two-ended 5.538 ms, 2 per trip 5.511, 3 per trip 5.592, 4 per trip 5.626 (absent positions are predicated off)
+#endif
 #ifndef H2J_FDCT_MIN_CTAS
 #define H2J_FDCT_MIN_CTAS 16  // resident single-warp CTAs per SM the register allocation is bounded for (16 -> 128 registers)
 #endif
@@ -316,18 +320,42 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
             // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
             // below it and its value, so the levels can be visited in any order.  Positions 1..31 (where nearly all of
-            // them are) are taken from both ends at once: two independent bit-scan -> load -> size -> atomic chains per
+            // them are) are taken two at a time: two independent bit-scan -> load -> size -> atomic chains per
             // iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
             unsigned int *hist = s_hist;
             unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
-            auto count = [&](int k, int below, int val) {
-                const int run = k - below - 1, nb = mag_bits(val);
+            auto count = [&](int k, int below, int val) {  // val != 0
+                const int run = k - below - 1;
+                unsigned top;  // size - 1: the + 1 rides in the address (size <= 15, no carry into the run nibble)
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(val)));
                 zrl += (unsigned)run >> 4;
-                atomicAdd(&hist[((run & 15) << 4) | nb], 1u);
+                atomicAdd(&hist[1 + (((run & 15) << 4) | (int)top)], 1u);
             };
             unsigned lo = mask_lo;
             const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
+#if H2J_K2_WALK
+            // H2J_K2_WALK positions per trip, taken from the low end, without a branch inside: the chains (position -> level
+            // -> size -> histogram) are independent, the ones a lane does not have are predicated off
+            int below = 0;
+            while (lo) {
+                const unsigned b0 = lo & (0u - lo);
+                lo ^= b0;
+                const unsigned b1 = lo & (0u - lo);
+                lo ^= b1;
+                const unsigned b2 = H2J_K2_WALK >= 3 ? lo & (0u - lo) : 0u;
+                lo ^= b2;
+                const unsigned b3 = H2J_K2_WALK >= 4 ? lo & (0u - lo) : 0u;
+                lo ^= b3;
+                const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1), k2 = 31 - __clz(b2), k3 = 31 - __clz(b3);  // -1: absent
+                const int v0 = (int)lv[2 * k0], v1 = (int)lv[2 * max(k1, 0)];
+                count(k0, below, v0);
+                if (b1) count(k1, k0, v1);
+                if (H2J_K2_WALK >= 3 && b2) count(k2, k1, (int)lv[2 * max(k2, 0)]);
+                if (H2J_K2_WALK >= 4 && b3) count(k3, k2, (int)lv[2 * max(k3, 0)]);
+                below = 31 - __clz(b0 | b1 | b2 | b3);
+            }
+#else
             int below_a = 0;   // ascending end: the non-zero position below the next one taken
             int kb = top_lo;   // descending end: the highest position still in `lo`
             while (lo) {
@@ -345,6 +373,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                 count(ka, below_a, val_a);
                 below_a = ka;
             }
+#endif
             int prev = top_lo;
             unsigned hi = mask_hi;
             while (hi) {
