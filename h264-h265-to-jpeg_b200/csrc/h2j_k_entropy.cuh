@@ -43,6 +43,11 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+#ifndef H2J_ENT_WALK
+#define H2J_ENT_WALK 2
+#endif
+constexpr int kWalkPerTrip = H2J_ENT_WALK;                   // K4a: non-zero levels a lane takes per trip of its walk (per 2048
+                                                             // frames: 1 -> 2.927 ms, 2 -> 2.758, 3 -> 2.834, 4 -> 2.907)
 constexpr int kUnitBlocks = 32;                              // one warp
 constexpr int kEntWarps = kEntThreads / 32;                  // units per CTA
 constexpr int kWarpWinWords = 256;                           // per-warp bit window: 8 Kibit
@@ -169,22 +174,30 @@ __device__ __forceinline__ unsigned walk_block(const int16_t *cb, unsigned mask_
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         unsigned mm = half ? mask_hi : mask_lo;
-        // two positions per trip: their position -> level -> size -> code look-ups are independent and overlap; only the
-        // emission is in order (the second one is predicated off when the lane has run out)
+        // kWalkPerTrip positions per trip: their position -> level -> size -> code look-ups are independent and overlap;
+        // only the emission is in order (positions a lane has run out of are predicated off)
         while (mm) {
-            const unsigned b0 = mm & (0u - mm);
-            mm ^= b0;
-            const unsigned b1 = mm & (0u - mm);
-            mm ^= b1;
-            const int p0 = 31 - __clz(b0), p1 = b1 ? 31 - __clz(b1) : p0;
-            const int k0 = half * 32 + p0, k1 = half * 32 + p1;
-            const int val0 = (int)cb[2 * p0 + half], val1 = (int)cb[2 * p1 + half];
-            const int nb0 = mag_bits(val0), nb1 = mag_bits(val1);
-            const int run0 = k0 - prev - 1, run1 = k1 - k0 - 1;
-            const uint32_t e0 = hac[((run0 & 15) << 4) | nb0], e1 = hac[((run1 & 15) << 4) | nb1];
-            code_one(run0, val0, nb0, e0);
-            if (b1) code_one(run1, val1, nb1, e1);
-            prev = k1;
+            unsigned b[kWalkPerTrip];
+            int k[kWalkPerTrip], val[kWalkPerTrip], nb[kWalkPerTrip], run[kWalkPerTrip];
+            uint32_t e[kWalkPerTrip];
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++) {
+                b[i] = mm & (0u - mm);
+                mm ^= b[i];
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++) {
+                const int p = (i == 0 || b[i]) ? 31 - __clz(b[i]) : k[i - 1] - half * 32;  // absent: the previous position again
+                k[i] = half * 32 + p;
+                val[i] = (int)cb[2 * p + half];
+                nb[i] = mag_bits(val[i]);
+                run[i] = k[i] - (i ? k[i - 1] : prev) - 1;
+                e[i] = hac[((run[i] & 15) << 4) | nb[i]];
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++)
+                if (i == 0 || b[i]) code_one(run[i], val[i], nb[i], e[i]);
+            prev = k[kWalkPerTrip - 1];
         }
     }
     if (prev < 63) {
