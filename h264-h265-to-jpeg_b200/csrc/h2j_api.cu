@@ -320,9 +320,15 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         ScopedTiming t(e, sl, "scan_place_kernel");
         const int n_units = (L.n_blocks + kUnitBlocks - 1) / kUnitBlocks;
         const int groups_per_frame = (n_units + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
-        scan_place_kernel<<<groups_per_frame * n, kPlaceThreads, 0, st>>>(L, sl.d_tabs, sl.d_state, sl.d_unit_info, e->units_cap, sl.d_stage,
-                                                                         e->stage_cap_words, sl.d_descs, groups_per_frame, sl.d_ticket, sl.d_scan,
-                                                                         e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
+        // fewer groups than two per SM: every group on four times as many warps
+        if ((long long)groups_per_frame * n < 2LL * e->sm_count)
+            scan_place_kernel<8><<<groups_per_frame * n, kPlaceGroupUnits / 8 * 32, 0, st>>>(L, sl.d_tabs, sl.d_state, sl.d_unit_info, e->units_cap, sl.d_stage,
+                                                                                   e->stage_cap_words, sl.d_descs, groups_per_frame, sl.d_ticket, sl.d_scan,
+                                                                                   e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
+        else
+            scan_place_kernel<32><<<groups_per_frame * n, kPlaceThreads, 0, st>>>(L, sl.d_tabs, sl.d_state, sl.d_unit_info, e->units_cap, sl.d_stage,
+                                                                              e->stage_cap_words, sl.d_descs, groups_per_frame, sl.d_ticket, sl.d_scan,
+                                                                              e->scan_cap_words, sl.d_chunk_ff, e->chunks_cap);
         e->launches++;
     }
     {

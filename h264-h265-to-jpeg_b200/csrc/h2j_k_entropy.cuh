@@ -358,14 +358,19 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
 
 // grid (groups_per_frame * frames), groups taken through a ticket so that every predecessor group is running.
 // Bit positions are 32-bit: h2j_create bounds max_jpeg_bytes to 256 MiB.
-__global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
+// UPW = units a warp concatenates: 32 (256 threads, throughput form) or 8 (1024 threads: the same group spread over four
+// times as many warps, for batches too small to fill the GPU with groups -- one 1080p frame is six groups, and a warp that
+// walks 32 units one after the other takes ~19 us).
+template <int UPW>
+__global__ void __launch_bounds__(kPlaceGroupUnits / UPW * 32) scan_place_kernel(FrameLayout L, FrameTab *__restrict__ tabs, FrameState *__restrict__ state,
                                                                    const unsigned long long *__restrict__ unit_info, int units_cap,
                                                                    const uint32_t *__restrict__ stage, long long stage_cap_words,
                                                                    unsigned long long *__restrict__ descs, int groups_per_frame,
                                                                    unsigned int *__restrict__ ticket, uint32_t *__restrict__ scan,
                                                                    long long scan_cap_words, unsigned int *__restrict__ chunk_ff, int chunks_cap)
 {
-    static_assert(kPlaceGroupUnits == kPlaceThreads, "one unit per thread in the scan");
+    static_assert(kPlaceGroupUnits == kPlaceThreads, "one unit per thread in the scan (the first 256 threads)");
+    static_assert(UPW == 32 || UPW == 8, "units per warp");
     __shared__ unsigned s_pos[kPlaceGroupUnits + 1];    // staging position of the unit; [0] = the unit in front of the group
     __shared__ unsigned s_len[kPlaceGroupUnits + 1];    // its bit length
     __shared__ unsigned s_excl[kPlaceGroupUnits + 1];   // exclusive bit prefix inside the frame; [n_here] = end of the group
@@ -384,15 +389,17 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
     const unsigned long long *info = unit_info + (long long)f * units_cap;
 
     // ---- lengths of the group's units, block scan ----
-    const unsigned long long rec = tid < n_here ? info[u0 + tid] : 0ull;
+    const unsigned long long rec = tid < n_here ? info[u0 + tid] : 0ull;  // (threads behind the first 256 carry zeros)
     // a unit that did not fit the staging buffer gets the top bit of its position: the frame is reported, not read
     const unsigned cap_w = (unsigned)min(stage_cap_words, (long long)0x7fffffff);
     auto checked_pos = [&](unsigned long long r) {
         const unsigned pos = unit_pos(r), nw = (unit_bits(r) + 31) >> 5;
         return (pos > cap_w || nw > cap_w - pos) ? (pos | 0x80000000u) : pos;
     };
-    s_pos[1 + tid] = checked_pos(rec);
-    s_len[1 + tid] = unit_bits(rec);
+    if (tid < kPlaceGroupUnits) {
+        s_pos[1 + tid] = checked_pos(rec);
+        s_len[1 + tid] = unit_bits(rec);
+    }
     if (tid == 0) {
         const unsigned long long rp = u0 > 0 ? info[u0 - 1] : 0ull;
         s_pos[0] = checked_pos(rp);
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
         const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 31 && warp < kPlaceThreads / 32) s_wsum[warp] = incl;
     __syncthreads();
     unsigned warp_off = 0, group_total = 0;
 #pragma unroll
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(kPlaceThreads) scan_place_kernel(FrameLayout L
             if (nff) atomicAdd(&cff[W >> kChunkShift], nff);
         } else overflow = true;
     };
-    const int ub = warp * 32, ue = min(ub + 32, n_here);
+    const int ub = warp * UPW, ue = min(ub + UPW, n_here);
     if (ub < ue) {
         unsigned P = s_excl[ub], c = P & 31, carry = 0;
         if (c) {  // the last c bits in front of P: the tail of the unit in front (never shorter than a word)
