@@ -82,6 +82,7 @@ struct h2j_encoder {
     int chunks_cap = 0;           // K5 chunks per frame
     int stuff_ctas = 32;          // K5 CTAs per frame
     int fdct_tiles_per_cta = 16;  // upper bound of consecutive K2 tiles one CTA walks
+    int force_fdct_tiles = 0;     // h2j_debug_set_knob("fdct_tiles_per_cta"): exactly this many, whatever the batch size
     size_t frame_bytes_cap = 0;
     uint8_t *d_qscale_lut = nullptr;
     char *d_comment = nullptr;
@@ -296,6 +297,7 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         int tiles_per_cta = (int)((long long)n_tiles * n * 3 / ((long long)e->sm_count * 16 * 4));
         tiles_per_cta = tiles_per_cta < 1 ? 1 : (tiles_per_cta > e->fdct_tiles_per_cta ? e->fdct_tiles_per_cta : tiles_per_cta);
         if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
+        if (e->force_fdct_tiles > 0) tiles_per_cta = e->force_fdct_tiles;
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
         const dim3 grid(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
@@ -383,6 +385,27 @@ int enqueue_pack_and_sizes(h2j_encoder *e, Slot &sl, bool pack)
     return H2J_OK;
 }
 
+// Every entry point works on the encoder's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define ON_DEVICE(e)                        \
+    DeviceGuard device_guard__((e)->s.device); \
+    CU(e, device_guard__.err)
+
 int check_slot(h2j_encoder *e, int slot)
 {
     if (!e) return H2J_ERR_INVALID_ARG;
@@ -429,6 +452,16 @@ void h2j_default_settings(h2j_settings *s)
 
 int h2j_abi_version(void) { return H2J_ABI_VERSION; }
 
+int h2j_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 const char *h2j_status_string(int status)
 {
     switch (status) {
@@ -439,6 +472,7 @@ const char *h2j_status_string(int status)
     case H2J_ERR_OUTPUT_TOO_SMALL: return "output buffer too small";
     case H2J_ERR_BUSY: return "slot busy / nothing to collect";
     case H2J_ERR_NOMEM: return "out of memory";
+    case H2J_ERR_BUFFER_TOO_SMALL: return "caller buffer too small (slot still collectable)";
     default: return "unknown status";
     }
 }
@@ -458,7 +492,7 @@ void h2j_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 void h2j_destroy(h2j_encoder *e)
 {
     if (!e) return;
-    cudaSetDevice(e->s.device);
+    DeviceGuard guard(e->s.device);
     for (auto &sl : e->slots) free_slot(sl);
     cudaFree(e->d_qscale_lut);
     cudaFree(e->d_comment);
@@ -491,7 +525,8 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
             return bail(err__ == cudaErrorMemoryAllocation ? H2J_ERR_NOMEM : H2J_ERR_CUDA);                          \
         }                                                                                                           \
     } while (0)
-    CUB(cudaSetDevice(s->device));
+    DeviceGuard device_guard(s->device);
+    CUB(device_guard.err);
     cudaDeviceProp prop;
     CUB(cudaGetDeviceProperties(&prop, s->device));
     e->sm_count = prop.multiProcessorCount;
@@ -578,7 +613,7 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
     if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
     if (frame_stride < tight_frame_bytes(width, height)) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     const uint8_t *pipe_src = nullptr;
@@ -606,7 +641,7 @@ int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, si
     const size_t fb = tight_frame_bytes(width, height);
     const size_t dstride = align_up(fb, 256);
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
     if (rc) return rc;
     sl.n = n;
@@ -654,7 +689,7 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
     if (!frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
     const size_t fb = tight_frame_bytes(width, height);
     if (frame_stride < fb) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     // device copy keeps frames at a 256-byte aligned stride so the vector-load paths apply
     const size_t dstride = align_up(fb, 256);
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
@@ -679,11 +714,23 @@ int h2j_slot_set_stream(h2j_encoder *e, int slot, void *cuda_stream)
     if (rc) return rc;
     Slot &sl = e->slots[slot];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
     if (sl.own_stream) CU(e, cudaStreamDestroy(sl.stream));
     sl.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     sl.own_stream = false;
+    return H2J_OK;
+}
+
+int h2j_slot_wait_event(h2j_encoder *e, int slot, void *cuda_event)
+{
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    if (!cuda_event) return fail(e, H2J_ERR_INVALID_ARG, "null event");
+    Slot &sl = e->slots[slot];
+    if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
+    ON_DEVICE(e);
+    CU(e, cudaStreamWaitEvent(sl.stream, reinterpret_cast<cudaEvent_t>(cuda_event), 0));
     return H2J_OK;
 }
 
@@ -702,7 +749,7 @@ int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, siz
     Slot &sl = e->slots[slot];
     if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
     if (!out || !offsets) return fail(e, H2J_ERR_INVALID_ARG, "null out/offsets");
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     if (!sl.packed) {  // submitted with h2j_submit_device: pack now
         ScopedTiming t(e, sl, "pack_kernel");
         pack_kernel<<<dim3(8, sl.n), 256, 0, sl.stream>>>(sl.d_out, (long long)e->out_cap, sl.d_offsets, sl.d_packed);
@@ -710,7 +757,6 @@ int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, siz
         sl.packed = true;
     }
     CU(e, cudaStreamSynchronize(sl.stream));
-    sl.busy = false;
     const size_t total = (size_t)sl.h_offsets[sl.n];
     int worst = H2J_OK;
     for (int i = 0; i <= sl.n; i++) offsets[i] = (size_t)sl.h_offsets[i];
@@ -718,10 +764,13 @@ int h2j_collect(h2j_encoder *e, int slot, uint8_t *out, size_t out_capacity, siz
         if (status) status[i] = sl.h_status[i];
         if (sl.h_status[i] != 0) worst = sl.h_status[i];
     }
-    if (total > out_capacity) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "batch needs %zu bytes, caller gave %zu", total, out_capacity);
+    // a short caller buffer loses nothing: offsets[] now holds the sizes, the slot stays collectable
+    if (total > out_capacity) return fail(e, H2J_ERR_BUFFER_TOO_SMALL, "batch needs %zu bytes, caller gave %zu (collect again with a larger buffer)", total, out_capacity);
     CU(e, cudaMemcpyAsync(out, sl.d_packed, total, cudaMemcpyDeviceToHost, sl.stream));
     CU(e, cudaEventRecord(sl.ev_done, sl.stream));
     CU(e, cudaStreamSynchronize(sl.stream));
+    sl.busy = false;
+    // frames that failed (status[i] != 0) have length 0 in offsets[]; the others are complete
     if (worst != H2J_OK) return fail(e, worst, "at least one frame failed: %s", h2j_status_string(worst));
     return H2J_OK;
 }
@@ -732,7 +781,7 @@ int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *
     if (rc) return rc;
     Slot &sl = e->slots[slot];
     if (!sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has nothing to collect", slot);
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
     sl.busy = false;
     int worst = H2J_OK;
@@ -761,7 +810,7 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
     // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels), uploaded in pieces of
     // ~512 KiB so that the DMA of one piece runs under the memcpy of the next
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     const size_t fb = tight_frame_bytes(width, height);
     const size_t dstride = align_up(fb, 256);
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
@@ -817,13 +866,15 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
                     uint8_t *out_y, uint8_t *out_u, uint8_t *out_v)
 {
     if (!e) return H2J_ERR_INVALID_ARG;
-    if (!planes || !strides || !out_y || !out_u || !out_v) return fail(e, H2J_ERR_INVALID_ARG, "null pointer");
+    if (!planes || !strides || !planes[0] || !planes[1] || !planes[2] || !out_y || !out_u || !out_v) return fail(e, H2J_ERR_INVALID_ARG, "null pointer");
     if (width < 2 || height < 2 || width > e->s.max_width || height > e->s.max_height)
         return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d outside the configured maximum", width, height);
+    if (range_mode != H2J_RANGE_PASSTHROUGH && range_mode != H2J_RANGE_LIMITED_TO_FULL) return fail(e, H2J_ERR_INVALID_ARG, "bad range_mode %d", range_mode);
     Slot &sl = e->slots[0];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
-    CU(e, cudaSetDevice(e->s.device));
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
+    if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
+    ON_DEVICE(e);
     uint8_t *p = sl.h_stage;
     for (int r = 0; r < height; r++) memcpy(p + (size_t)r * width, planes[0] + (size_t)r * strides[0], width);
     p += (size_t)width * height;
@@ -857,7 +908,7 @@ int h2j_debug_frame_info(h2j_encoder *e, int slot, int frame, h2j_frame_info *in
     if (rc) return rc;
     Slot &sl = e->slots[slot];
     if (!info || frame < 0 || frame >= sl.n) return fail(e, H2J_ERR_INVALID_ARG, "bad frame index %d", frame);
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
     FrameTab t;
     FrameState st;
@@ -887,7 +938,7 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     if (!out || frame < 0 || frame >= sl.n) return fail(e, H2J_ERR_INVALID_ARG, "bad frame index %d", frame);
     const size_t need = (size_t)sl.L.n_blocks * 64;
     if (out_elems < need) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "need %zu int16 elements", need);
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
     // tile images -> dense blocks; halfword 0 of a record is the DC difference, so the levels are rebuilt by
     // running the encoder's predictors (one per component, reset to 128) over the blocks in coding order
@@ -906,6 +957,26 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     return H2J_OK;
 }
 
+int h2j_debug_read_device(h2j_encoder *e, const void *d_src, void *dst, size_t bytes)
+{
+    if (!e) return H2J_ERR_INVALID_ARG;
+    if (!d_src || !dst) return fail(e, H2J_ERR_INVALID_ARG, "null pointer");
+    ON_DEVICE(e);
+    CU(e, cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return H2J_OK;
+}
+
+int h2j_debug_set_knob(h2j_encoder *e, const char *name, int value)
+{
+    if (!e || !name) return H2J_ERR_INVALID_ARG;
+    if (!strcmp(name, "fdct_tiles_per_cta")) {
+        if (value < 0 || value > 4096) return fail(e, H2J_ERR_INVALID_ARG, "fdct_tiles_per_cta %d out of range", value);
+        e->force_fdct_tiles = value;
+        return H2J_OK;
+    }
+    return fail(e, H2J_ERR_INVALID_ARG, "unknown knob %s", name);
+}
+
 int h2j_set_profile(h2j_encoder *e, int on)
 {
     if (!e) return H2J_ERR_INVALID_ARG;
@@ -918,7 +989,7 @@ int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, 
     int rc = check_slot(e, slot);
     if (rc) return rc;
     Slot &sl = e->slots[slot];
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
     int n = 0;
     for (int i = 0; i < sl.timings_used && n < cap; i++, n++) {
@@ -936,7 +1007,7 @@ int h2j_slot_total_ms(h2j_encoder *e, int slot, float *ms)
     if (rc) return rc;
     Slot &sl = e->slots[slot];
     if (!ms) return fail(e, H2J_ERR_INVALID_ARG, "null ms");
-    CU(e, cudaSetDevice(e->s.device));
+    ON_DEVICE(e);
     CU(e, cudaEventSynchronize(sl.ev_done));
     CU(e, cudaEventElapsedTime(ms, sl.ev_begin, sl.ev_done));
     return H2J_OK;

@@ -1,4 +1,4 @@
-// Device side of h2j_b200: the YUV -> JPEG stage of the reference (src/Encoder.cpp:89-297, i.e. libavcodec's
+// Device side of h2j_b200: the YUV -> JPEG stage of the reference (src/Encoder.cpp:104-308, i.e. libavcodec's
 // mjpeg encoder as the reference configures it) as sm_100a kernels.  One launch handles a batch of same-sized
 // frames; frames never interact, so the batch index is simply a grid dimension.
 //

@@ -17,6 +17,14 @@ namespace h2j {
 
 struct HuffPair { int a, b; };  // {value, prob} or {code, length}
 
+// tools/microbench/k3_phases.cu: cycle stamps of one table's phases (thread 0 of the CTA that builds table 2 of frame 0)
+#ifdef H2J_K3_CLOCKS
+__device__ long long g_k3_clocks[16];
+#define K3_STAMP(i) do { if (gt == 0 && S->stamp_on) g_k3_clocks[i] = clock64(); } while (0)
+#else
+#define K3_STAMP(i) do { } while (0)
+#endif
+
 __device__ void av_qsort_pairs(HuffPair *p, int num)
 {
 #define H2J_CMP(x, y) ((x)->b - (y)->b)
@@ -120,6 +128,9 @@ struct HuffScratch {
     int warp_tot[4];
     int first_code[18], first_index[18];
     unsigned int bits_cnt[17];
+#ifdef H2J_K3_CLOCKS
+    int stamp_on;
+#endif
 };
 
 __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kHuffGroup) : "memory"); }
@@ -152,6 +163,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
                                 int *g_nvals, uint32_t *g_hcode)
 {
     // ---- ff_mjpeg_encode_huffman_close: used symbols in increasing value order, plus the dummy (256, 0) ----
+    K3_STAMP(0);
     const int h0 = (int)hist[2 * gt], h1 = (int)hist[2 * gt + 1];
     int nval;
     int pos = group_excl_scan((h0 != 0) + (h1 != 0), gt, group, S->warp_tot, &nval);
@@ -160,8 +172,10 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
     if (gt == 0) { S->sorted[nval].a = 256; S->sorted[nval].b = 0; }
     const int size = nval + 1;
     group_sync(group);
+    K3_STAMP(1);
     if (gt == 0) av_qsort_pairs(S->sorted, size);
     group_sync(group);
+    K3_STAMP(2);
 
     // ---- ff_mjpegenc_huffman_compute_bits, max_length 16: levels 0..15 take symbols, level 16 only packages ----
     for (int k = gt; k <= size; k += kHuffGroup) {
@@ -207,6 +221,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
         cur ^= 1;
     }
     group_sync(group);
+    K3_STAMP(3);
     // ---- back-trace: how many symbols each level contributes to the first min(size-1, nitems) items ----
     if (gt == 0) {
         int p = size - 1 < n_prev ? size - 1 : n_prev;
@@ -236,8 +251,10 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
         // tot == nval: every used symbol receives a code
     }
     group_sync(group);
+    K3_STAMP(4);
     if (gt == 0) av_qsort_pairs(S->distinct, nval);
     group_sync(group);
+    K3_STAMP(5);
     // ---- BITS / HUFFVAL, then ff_mjpeg_build_huffman_codes ----
     for (int i = gt; i < 256; i += kHuffGroup) {
         g_vals[i] = i < nval ? (uint8_t)S->distinct[i].a : 0;
@@ -262,6 +279,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
         const int code = S->first_code[len] + (i - S->first_index[len]);
         g_hcode[S->distinct[i].a] = ((uint32_t)code << 5) | (uint32_t)len;
     }
+    K3_STAMP(6);
 }
 
 // Byte i of the picture header: SOI, COM, DQT, DHT (4 tables), SOF0, SOS (ff_mjpeg_encode_picture_header).
@@ -334,6 +352,10 @@ __global__ void __launch_bounds__(kHuffGroup) huffman_kernel(FrameLayout L, Fram
     const int slot = blockIdx.x / n_frames, f = blockIdx.x - slot * n_frames;
     const int table = slot ^ 2;  // 2, 3 (AC luma, AC chroma), then 0, 1 (DC)
     FrameTab *T = tabs + f;
+#ifdef H2J_K3_CLOCKS
+    if (tid == 0) scratch.stamp_on = (table == 2 && f == 0);
+    __syncthreads();
+#endif
     build_one_table(state[f].hist[table], &scratch, tid, 0, T->bits[table], T->vals[table], &T->nvals[table], T->hcode[table]);
     __threadfence();
     __syncthreads();

@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(128) convert_pad_kernel(const uint8_t *__restr
     if (x0 >= padw) return;
     const uint8_t *row = P + (long long)min(y, ph - 1) * pitch;
     uint8_t px[16];
-    if (L.aligned16 && x0 + 16 <= pw) {
+    // the 128-bit path is decided per row: L.aligned16 only speaks for the luma rows, and a chroma pitch of w/2 with
+    // w = 16 (mod 32) (720, 848, 1360 ...) puts every odd chroma row 8 bytes off a 16-byte boundary
+    if (x0 + 16 <= pw && ((uintptr_t)(row + x0) & 15u) == 0) {
         const uint4 v = ldg128(row + x0);
         const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll

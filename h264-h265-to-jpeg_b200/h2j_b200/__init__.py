@@ -4,7 +4,7 @@ This is the thin Python face used by tests/, bench.py and __graft_entry__.py.  I
 ``h264-h265-to-jpeg_b200/lib/libh2j_b200.so`` (built by ``__graft_entry__.build()``) and fails loudly when the
 library is missing or no CUDA device is usable -- there is no CPU path behind this module.
 
-Reference surface being replaced: ``Encoder::yuv2Jpeg`` (reference src/Encoder.cpp:89) -- see
+Reference surface being replaced: ``Encoder::yuv2Jpeg`` (reference src/Encoder.cpp:104) -- see
 ``Encoder.yuv2jpeg`` below for the same call shape on numpy planes.
 """
 from __future__ import annotations
@@ -27,6 +27,7 @@ ERR_UNSUPPORTED = -3
 ERR_OUTPUT_TOO_SMALL = -4
 ERR_BUSY = -5
 ERR_NOMEM = -6
+ERR_BUFFER_TOO_SMALL = -7
 
 RANGE_PASSTHROUGH = 0
 RANGE_LIMITED_TO_FULL = 1
@@ -75,6 +76,7 @@ EXPORTS = [
     "h2j_encode_frame", "h2j_submit_host", "h2j_submit_device", "h2j_submit_device_nv12", "h2j_collect", "h2j_collect_device", "h2j_wait",
     "h2j_alloc_pinned", "h2j_free_pinned", "h2j_convert_pad", "h2j_debug_frame_info", "h2j_debug_coefficients",
     "h2j_slot_kernel_ms", "h2j_set_profile", "h2j_slot_total_ms", "h2j_kernel_launches", "h2j_slot_set_stream",
+    "h2j_slot_wait_event", "h2j_device_count", "h2j_debug_set_knob", "h2j_debug_read_device",
 ]
 
 _lib = None
@@ -110,6 +112,10 @@ def load_library() -> C.CDLL:
     lib.h2j_collect_device.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz), C.POINTER(ci)]
     lib.h2j_wait.argtypes = [vp, ci]
     lib.h2j_slot_set_stream.argtypes = [vp, ci, vp]
+    lib.h2j_slot_wait_event.argtypes = [vp, ci, vp]
+    lib.h2j_device_count.restype = ci
+    lib.h2j_debug_set_knob.argtypes = [vp, C.c_char_p, ci]
+    lib.h2j_debug_read_device.argtypes = [vp, vp, vp, sz]
     lib.h2j_alloc_pinned.argtypes = [sz]
     lib.h2j_alloc_pinned.restype = vp
     lib.h2j_free_pinned.argtypes = [vp]
@@ -192,7 +198,7 @@ class BatchResult:
 
 
 class Encoder:
-    """GPU JPEG encoder.  ``yuv2jpeg`` mirrors reference ``Encoder::yuv2Jpeg`` (src/Encoder.cpp:89)."""
+    """GPU JPEG encoder.  ``yuv2jpeg`` mirrors reference ``Encoder::yuv2Jpeg`` (src/Encoder.cpp:104)."""
 
     def __init__(self, max_width: int = 1920, max_height: int = 1088, max_batch: int = 16, n_slots: int = 2, device: int = 0,
                  range_mode: int = RANGE_PASSTHROUGH, fixed_qscale: int = 0, max_jpeg_bytes: int = 0,
@@ -234,6 +240,12 @@ class Encoder:
         if rc < 0:
             raise H2JError(rc, (self._lib.h2j_last_error(self._h) or b"").decode())
 
+    @staticmethod
+    def _check_chroma(w: int, h: int, u: np.ndarray, v: np.ndarray) -> None:
+        want = ((h + 1) // 2, (w + 1) // 2)
+        if u.shape != want or v.shape != want:
+            raise H2JError(ERR_INVALID_ARG, f"chroma planes must be {want[0]}x{want[1]} (ceil-halved luma), got {u.shape} / {v.shape}")
+
     # -- single frame, the Encoder::yuv2Jpeg shape --------------------------------------------
     def yuv2jpeg(self, y: np.ndarray, u: np.ndarray, v: np.ndarray) -> bytes:
         """One 8-bit 4:2:0 frame (2-D uint8 planes, any row stride) -> JPEG bytes."""
@@ -241,12 +253,27 @@ class Encoder:
             if p.dtype != np.uint8 or p.ndim != 2 or p.strides[1] != 1:
                 raise H2JError(ERR_INVALID_ARG, "planes must be 2-D uint8 arrays with contiguous rows")
         h, w = y.shape
+        self._check_chroma(w, h, u, v)
         planes = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
         strides = (C.c_int * 3)(y.strides[0], u.strides[0], v.strides[0])
         out = np.empty(self.out_capacity, np.uint8)
         n = C.c_size_t(0)
         self._check(self._lib.h2j_encode_frame(self._h, planes, strides, w, h, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value].tobytes()
+
+    def yuv2jpeg_into(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, out: Optional[np.ndarray] = None) -> int:
+        """Same call, JPEG bytes into a caller buffer (or a buffer kept by this object: ``self.last_out``); returns the
+        size.  Nothing is allocated per call -- the form to time."""
+        if out is None:
+            if getattr(self, "last_out", None) is None:
+                self.last_out = np.empty(self.out_capacity, np.uint8)
+            out = self.last_out
+        h, w = y.shape
+        planes = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
+        strides = (C.c_int * 3)(y.strides[0], u.strides[0], v.strides[0])
+        n = C.c_size_t(0)
+        self._check(self._lib.h2j_encode_frame(self._h, planes, strides, w, h, out.ctypes.data, out.size, C.byref(n)))
+        return int(n.value)
 
     # -- batches ----------------------------------------------------------------------------------
     def submit_host(self, slot: int, frames_ptr: int, frame_stride: int, n: int, width: int, height: int) -> None:
@@ -263,6 +290,16 @@ class Encoder:
         self._check(self._lib.h2j_submit_device_nv12(self._h, slot, d_frames_ptr, frame_stride, pitch, uv_offset, n, width, height))
         self._n_in_slot[slot] = n
 
+    def read_device(self, d_ptr: int, nbytes: int) -> bytes:
+        """Bytes of device memory on the encoder's device (e.g. one JPEG left there by collect_device)."""
+        out = np.empty(nbytes, np.uint8)
+        self._check(self._lib.h2j_debug_read_device(self._h, d_ptr, out.ctypes.data, nbytes))
+        return out.tobytes()
+
+    def set_knob(self, name: str, value: int) -> None:
+        """Launch-shape override for tests (h2j_debug_set_knob); results never depend on it."""
+        self._check(self._lib.h2j_debug_set_knob(self._h, name.encode(), value))
+
     def set_profile(self, on: bool) -> None:
         """Per-kernel event brackets for the batches submitted from now on."""
         self._check(self._lib.h2j_set_profile(self._h, 1 if on else 0))
@@ -271,22 +308,33 @@ class Encoder:
         """Enqueue the slot's work on a caller-owned stream (raw cudaStream_t handle)."""
         self._check(self._lib.h2j_slot_set_stream(self._h, slot, cuda_stream))
 
+    def wait_event(self, slot: int, cuda_event: int) -> None:
+        """Order the slot's next work behind a CUDA event (raw cudaEvent_t, e.g. ``torch.cuda.Event().cuda_event``)
+        recorded behind whatever produces the next batch's device input."""
+        self._check(self._lib.h2j_slot_wait_event(self._h, slot, cuda_event))
+
     def wait(self, slot: int) -> None:
         self._check(self._lib.h2j_wait(self._h, slot))
 
-    def collect_into(self, slot: int, out_ptr: int, out_capacity: int) -> Tuple[np.ndarray, np.ndarray]:
-        """Copy the slot's JPEGs packed into caller memory; returns (offsets[n+1], status[n])."""
+    def collect_into(self, slot: int, out_ptr: int, out_capacity: int, strict: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        """Copy the slot's JPEGs packed into caller memory; returns (offsets[n+1], status[n]).  A frame that failed has
+        length 0 and a non-zero status; with strict=True (default) that raises, the good frames are still in the buffer.
+        ERR_BUFFER_TOO_SMALL (caller buffer short) leaves the slot collectable: H2JError.offsets holds the sizes."""
         n = self._n_in_slot[slot]
         offs = (C.c_size_t * (n + 1))()
         st = (C.c_int * n)()
         rc = self._lib.h2j_collect(self._h, slot, out_ptr, out_capacity, offs, st)
-        self._check(rc)
-        return np.frombuffer(offs, dtype=np.uintp).copy(), np.frombuffer(st, dtype=np.intc).copy()
+        offsets, status = np.frombuffer(offs, dtype=np.uintp).copy(), np.frombuffer(st, dtype=np.intc).copy()
+        if rc == ERR_BUFFER_TOO_SMALL or (rc < 0 and (strict or not status.any())):
+            err = H2JError(rc, (self._lib.h2j_last_error(self._h) or b"").decode())
+            err.offsets, err.frame_status = offsets, status
+            raise err
+        return offsets, status
 
-    def collect(self, slot: int) -> BatchResult:
+    def collect(self, slot: int, strict: bool = True) -> BatchResult:
         n = self._n_in_slot[slot]
-        out = np.empty(self.out_capacity * n, np.uint8)
-        offs, st = self.collect_into(slot, out.ctypes.data, out.size)
+        out = np.empty((self.out_capacity + 15) // 16 * 16 * n, np.uint8)
+        offs, st = self.collect_into(slot, out.ctypes.data, out.size, strict=strict)
         return BatchResult([out[int(offs[i]): int(offs[i + 1])].tobytes() for i in range(n)], [int(x) for x in st])
 
     def collect_device(self, slot: int) -> Tuple[int, int, np.ndarray, np.ndarray]:
@@ -308,6 +356,7 @@ class Encoder:
     # -- kernel 1 on its own -----------------------------------------------------------------
     def convert_pad(self, y: np.ndarray, u: np.ndarray, v: np.ndarray, range_mode: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         h, w = y.shape
+        self._check_chroma(w, h, u, v)
         mw, mh = (w + 15) // 16, (h + 15) // 16
         oy = np.empty((mh * 16, mw * 16), np.uint8)
         ou = np.empty((mh * 8, mw * 8), np.uint8)

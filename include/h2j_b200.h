@@ -3,12 +3,12 @@
  * BornToDeath/h264-h265-to-jpeg, behind a plain C ABI.
  *
  * What it replaces in the reference (file:line in /root/reference):
- *   src/Encoder.cpp:89-297   Encoder::yuv2Jpeg(AVFrame*)  — avcodec "mjpeg" encoder opened with
- *                            pix_fmt YUVJ420P (:150), time_base 1/25 (:190), defaults otherwise,
- *                            avcodec_send_frame (:239) / avcodec_receive_packet (:248), raw "mjpeg" muxer
- *                            write (:262), bytes gathered through writeCallback (:27) into a 2 MiB buffer
- *                            (src/Common.h:15 HEAP_SIZE) and saved with saveJpegtoFile (:336).
- *   src/Decoder.cpp:319      the only call site: Encoder(outputFilePath).yuv2Jpeg(frame).
+ *   src/Encoder.cpp:104-308  Encoder::yuv2Jpeg(AVFrame*)  — avcodec "mjpeg" encoder opened with
+ *                            pix_fmt YUVJ420P (:162), time_base 1/25 (:201), defaults otherwise,
+ *                            avcodec_send_frame (:250) / avcodec_receive_packet (:259), raw "mjpeg" muxer
+ *                            write (:278), bytes gathered through writeCallback (:27) into a 2 MiB buffer
+ *                            (src/Common.h:16 HEAP_SIZE) and saved with saveJpegtoFile (:338).
+ *   src/Decoder.cpp:349      the only call site: Encoder(outputFilePath).yuv2Jpeg(frame).
  * Everything in front of it (src/Decoder.cpp libavformat/libavcodec H.264/H.265 decode) and the public
  * surface (export_inc/IDecoder.h, src/jni/...) stay the reference's own code.
  *
@@ -20,6 +20,7 @@
  *
  * Threading: an h2j_encoder is not internally synchronised.  Use it from one thread at a time (or one encoder
  * per thread); different encoders are independent.  Work of different slots of one encoder overlaps on the GPU.
+ * Every entry point selects the encoder's device for the duration of the call and restores the caller's current device.
  */
 #ifndef H2J_B200_H
 #define H2J_B200_H
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H2J_ABI_VERSION 1
+#define H2J_ABI_VERSION 2
 
 typedef enum h2j_status {
     H2J_OK = 0,
@@ -40,13 +41,15 @@ typedef enum h2j_status {
     H2J_ERR_UNSUPPORTED = -3,     /* geometry outside max_width/max_height, width or height < 2 or > 65500 */
     H2J_ERR_OUTPUT_TOO_SMALL = -4,/* a JPEG did not fit max_jpeg_bytes / the caller's buffer */
     H2J_ERR_BUSY = -5,            /* slot already has a batch in flight, or nothing to collect */
-    H2J_ERR_NOMEM = -6
+    H2J_ERR_NOMEM = -6,
+    H2J_ERR_BUFFER_TOO_SMALL = -7 /* h2j_collect: the CALLER's buffer is shorter than the batch; offsets[] holds the
+                                     sizes, the slot stays collectable -- call again with a larger buffer */
 } h2j_status;
 
 /* How the planes are interpreted before encoding. */
 typedef enum h2j_range_mode {
     /* Planes go to the encoder as they are.  This is what reference src/Encoder.cpp does: it never calls
-     * sws_scale; a yuv420p AVFrame is handed to an encoder opened as yuvj420p (Encoder.cpp:150, :239). */
+     * sws_scale; a yuv420p AVFrame is handed to an encoder opened as yuvj420p (Encoder.cpp:162, :250). */
     H2J_RANGE_PASSTHROUGH = 0,
     /* yuv420p (limited) -> yuvj420p (full) first, bit-exact with libswscale 5.8.100's unscaled
      * lumRangeToJpeg/chrRangeToJpeg path (what a sws_scale call in front of the encoder would produce). */
@@ -78,10 +81,12 @@ void h2j_destroy(h2j_encoder *e);
 const char *h2j_last_error(const h2j_encoder *e); /* e may be NULL: error of the last failed h2j_create */
 const char *h2j_status_string(int status);
 int h2j_abi_version(void);
+/* CUDA devices this process can use (0 when there is none or the driver cannot be initialised). */
+int h2j_device_count(void);
 
 /*
  * One frame, host planes in, JPEG bytes out, synchronous — the drop-in for
- * Encoder::yuv2Jpeg() (reference src/Encoder.cpp:89).  planes/strides follow AVFrame.data/.linesize for
+ * Encoder::yuv2Jpeg() (reference src/Encoder.cpp:104).  planes/strides follow AVFrame.data/.linesize for
  * an 8-bit 4:2:0 planar frame: plane 0 is width x height, planes 1/2 are ceil(width/2) x ceil(height/2).
  * Uses slot 0; the planes are staged through pinned memory and copied asynchronously.
  */
@@ -96,11 +101,21 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
  *                    kernels and nothing else are enqueued on the slot's stream.  Returns immediately.
  * h2j_submit_device: frames already live in device memory on the encoder's device.
  * h2j_collect:       waits for the slot, copies the JPEGs back packed one after another into `out`
- *                    (offsets[i] .. offsets[i+1]) and frees the slot.  offsets has n+1 entries.
+ *                    (offsets[i] .. offsets[i+1]) and frees the slot.  offsets has n+1 entries.  A frame that failed
+ *                    (status[i] != 0, e.g. its JPEG outgrew max_jpeg_bytes) has length 0; the others are complete and the
+ *                    call returns the failed frames' status.  If `out` itself is too short for the batch the call returns
+ *                    H2J_ERR_BUFFER_TOO_SMALL with offsets[] filled in and the slot still collectable.
  * h2j_collect_device:waits for the slot and only reports where the JPEGs are on the device: frame i is
  *                    at (*d_out) + i * (*d_frame_capacity), sizes[i] bytes long (sizes is a host array).
  *                    The memory stays valid until the slot is submitted to again.
  * status[i] (optional, may be NULL) receives a per-frame h2j_status.
+ *
+ * Stream ordering of device inputs: the kernels of a slot run on the slot's own (non-blocking) stream, or on the stream
+ * given with h2j_slot_set_stream.  h2j_submit_device / h2j_submit_device_nv12 read the caller's device memory on THAT
+ * stream; nothing orders them behind work of other streams.  A caller whose frames are produced on another stream (a
+ * decoder's, torch's current stream) must, before submitting, either synchronise that stream, or make the slot use it
+ * (h2j_slot_set_stream), or record an event behind the producer and hand it to h2j_slot_wait_event.  The same holds
+ * for reusing the input memory: it may be overwritten once the slot has been collected (or h2j_wait returned).
  */
 int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t frame_stride, int n, int width,
                     int height);
@@ -121,6 +136,9 @@ int h2j_collect_device(h2j_encoder *e, int slot, const uint8_t **d_out, size_t *
 /* Make the slot enqueue on a caller-owned CUDA stream (a cudaStream_t, e.g. torch.cuda.Stream().cuda_stream)
  * instead of its own, so the caller can bracket the work with its own events.  The slot must be idle. */
 int h2j_slot_set_stream(h2j_encoder *e, int slot, void *cuda_stream);
+/* Make everything submitted to the (idle) slot from now on wait, on the device, for a CUDA event (a cudaEvent_t recorded
+ * by the caller behind the work that produces the next batch's input).  No host synchronisation. */
+int h2j_slot_wait_event(h2j_encoder *e, int slot, void *cuda_event);
 /* Block until the slot's stream is idle without collecting (timing helper). */
 int h2j_wait(h2j_encoder *e, int slot);
 
@@ -156,6 +174,14 @@ int h2j_debug_frame_info(h2j_encoder *e, int slot, int frame, h2j_frame_info *in
 /* Quantised levels of one frame: mcu_w*mcu_h*6 blocks in MCU order (Y0 Y1 Y2 Y3 Cb Cr), 64 int16 each in
  * zigzag order (index 0 = quantised DC level, not the difference). */
 int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, size_t out_elems);
+
+/* Synchronous copy of `bytes` bytes of device memory on the encoder's device (e.g. a JPEG reported by h2j_collect_device)
+ * to host memory: lets callers without a CUDA binding of their own look at device-resident results. */
+int h2j_debug_read_device(h2j_encoder *e, const void *d_src, void *dst, size_t bytes);
+/* Launch-shape overrides for tests that must reach code paths a small batch would not take on its own.  Results never
+ * depend on a knob.  "fdct_tiles_per_cta": consecutive 16-MCU tiles one CTA of the FDCT kernel walks (0 = automatic:
+ * 1 for small batches, up to 16 for large ones). */
+int h2j_debug_set_knob(h2j_encoder *e, const char *name, int value);
 
 /* With settings.profile != 0: milliseconds each kernel of the slot's last batch took, measured with CUDA
  * events on the stream the kernels were launched on.  names/ms have `cap` entries; returns the count. */

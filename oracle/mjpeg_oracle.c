@@ -3,10 +3,10 @@
  * bench.py's cpu_baseline / --impl reference legs may load this.
  *
  * CPU restatement (plain C, scalar) of the YUV -> JPEG stage the reference runs:
- *   reference src/Encoder.cpp:89-297  Encoder::yuv2Jpeg() opens libavcodec's "mjpeg" encoder with
- *   pix_fmt = AV_PIX_FMT_YUVJ420P (Encoder.cpp:150), time_base 1/25 (Encoder.cpp:190), every other
- *   option at its default, sends ONE frame (Encoder.cpp:239) and writes the packet through the raw
- *   "mjpeg" muxer (Encoder.cpp:262).  No sws_scale call exists in the reference: the decoded planes are
+ *   reference src/Encoder.cpp:104-308  Encoder::yuv2Jpeg() opens libavcodec's "mjpeg" encoder with
+ *   pix_fmt = AV_PIX_FMT_YUVJ420P (Encoder.cpp:162), time_base 1/25 (Encoder.cpp:201), every other
+ *   option at its default, sends ONE frame (Encoder.cpp:250) and writes the packet through the raw
+ *   "mjpeg" muxer (Encoder.cpp:278).  No sws_scale call exists in the reference: the decoded planes are
  *   handed to the encoder as they are.
  *
  * The algorithm itself lives in a third-party dependency that is NOT in /root/reference as source:

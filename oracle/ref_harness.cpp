@@ -8,7 +8,7 @@
 //   * the C restatement in oracle/mjpeg_oracle.c can be pinned against the real thing,
 //   * golden fixtures under tests/golden/ can be generated (tests/golden/make_golden.py),
 //   * bench.py --impl reference / cpu_baseline(kind="reference") can time the real
-//     reference YUV->JPEG stage (Encoder::yuv2Jpeg, reference src/Encoder.cpp:89).
+//     reference YUV->JPEG stage (Encoder::yuv2Jpeg, reference src/Encoder.cpp:104).
 // Nothing in the product path links or loads this file.
 #include <cstdint>
 #include <cstdio>
@@ -66,7 +66,7 @@ AVFrame *make_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const ui
 
 extern "C" {
 
-// Reference YUV->JPEG stage: Encoder(out).yuv2Jpeg(frame)  (reference src/Encoder.cpp:89-297).
+// Reference YUV->JPEG stage: Encoder(out).yuv2Jpeg(frame)  (reference src/Encoder.cpp:104-308).
 // Planes are tightly described by (ptr, stride); chroma planes are ceil(w/2) x ceil(h/2).
 // Returns 1 on success (the reference's bool), 0 on failure.
 int ref_yuv2jpeg_file(const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
@@ -195,11 +195,12 @@ int ref_sws_limited_to_full(const uint8_t *y, const uint8_t *u, const uint8_t *v
 
 // N same-sized tight I420 frames (frame_stride bytes apart), `threads` host threads, each thread running the
 // reference's Encoder::yuv2Jpeg on frames tid, tid+threads, ... — one fresh Encoder per frame, exactly as
-// reference src/Decoder.cpp:319 does — writing to tmpfs.  sizes[i] receives each JPEG's size (0 on failure).
+// reference src/Decoder.cpp:349 does — writing to tmpfs.  sizes[i] receives each JPEG's size (0 on failure).
 // Returns the number of frames that encoded.
 }  // extern "C"
 #include <pthread.h>
 #include <sys/stat.h>
+#include <time.h>
 namespace {
 struct MtJob {
     const uint8_t *frames; long stride; int n, w, h, tid, nthreads; long *sizes; int ok;
@@ -243,6 +244,38 @@ int ref_yuv2jpeg_batch_mt(const uint8_t *frames, long frame_stride, int n, int w
     }
     int ok = 0;
     for (int t = 0; t < threads; t++) { pthread_join(th[t], nullptr); ok += jobs[t].ok; }
+    return ok;
+}
+
+// The reference's own harness loop (main.cpp:37-65), timed: n_calls x IDecoder::getInstance()->H265ToJpeg(in, out) dealt to
+// `threads` caller threads; call i writes <out_prefix><i>.jpeg.  Returns the number of successful calls.
+int ref_h265_loop(const char *in_path, const char *out_prefix, int n_calls, int threads, int quiet, double *seconds)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 512) threads = 512;
+    StdoutSilencer s(quiet != 0);
+    struct LoopJob { const char *in, *prefix; int n, tid, nthreads, ok; };
+    LoopJob jobs[512];
+    pthread_t th[512];
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = LoopJob{in_path, out_prefix, n_calls, t, threads, 0};
+        pthread_create(&th[t], nullptr, [](void *arg) -> void * {
+            LoopJob *j = static_cast<LoopJob *>(arg);
+            char out[512];
+            for (int i = j->tid; i < j->n; i += j->nthreads) {
+                snprintf(out, sizeof out, "%s%d.jpeg", j->prefix, i);
+                auto d = IDecoder::getInstance();
+                if (d && d->H265ToJpeg(j->in, out)) j->ok++;
+            }
+            return nullptr;
+        }, &jobs[t]);
+    }
+    int ok = 0;
+    for (int t = 0; t < threads; t++) { pthread_join(th[t], nullptr); ok += jobs[t].ok; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     return ok;
 }
 

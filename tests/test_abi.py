@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/h2j_b200.h but not exported"
     assert set(h2j_b200.EXPORTS) <= set(names)
-    assert lib.h2j_abi_version() == 1
+    assert lib.h2j_abi_version() == 2
 
 
 def test_status_strings_and_defaults():

@@ -55,3 +55,34 @@ def test_reference_arm_line_has_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_sample_indices_hold_first_last_and_stay_in_range():
+    import bench
+
+    for n, c in ((2048, 16), (64, 3), (2, 16), (1, 4)):
+        pick = bench.sample_indices(n, c, seed=n)
+        assert pick[0] == 0 and pick[-1] == n - 1 and len(pick) == min(max(c, len({0, n - 1})), n) and len(set(pick)) == len(pick)
+        assert all(0 <= i < n for i in pick)
+
+
+def test_rank_to_device_spreads_only_when_gpus_are_left_over(monkeypatch):
+    import bench
+
+    class FakeCuda:
+        def __init__(self, n):
+            self.n = n
+
+        def device_count(self):
+            return self.n
+
+    class FakeTorch:
+        def __init__(self, n):
+            self.cuda = FakeCuda(n)
+
+    assert [bench.rank_to_device(FakeTorch(8), r, 4)[0] for r in range(4)] == [0, 2, 4, 6]
+    assert [bench.rank_to_device(FakeTorch(8), r, 2)[0] for r in range(2)] == [0, 4]
+    assert [bench.rank_to_device(FakeTorch(8), r, 8)[0] for r in range(8)] == list(range(8))
+    assert [bench.rank_to_device(FakeTorch(2), r, 2)[0] for r in range(2)] == [0, 1]
+    monkeypatch.setenv("H2J_BENCH_SPREAD", "0")
+    assert [bench.rank_to_device(FakeTorch(8), r, 2)[0] for r in range(2)] == [0, 1]

@@ -1,6 +1,6 @@
 """GPU suite: the boundary.  (1) host/Encoder.cpp -- the C++ mirror of the reference's Encoder class -- through its
 C shim; (2) the DROP-IN: the reference's own src/Decoder.cpp + JNI bridge compiled against this repo's Encoder
-(host/Makefile target `dropin`), driven through the unchanged IDecoder::H265ToJpeg(in, out) on the reference's own
+(host/Makefile target `dropin`, with this repo's Encoder.h force-included in place of the reference's), driven through the unchanged IDecoder::H265ToJpeg(in, out) on the reference's own
 test/img fixtures (copied next to the .so at build time), compared byte for byte with what the unmodified
 reference (oracle/_ref/libh2j_ref.so) writes for the same file."""
 import ctypes as C
@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST_SO = os.path.join(ROOT, "h264-h265-to-jpeg_b200", "lib", "libh2j_host.so")
-DROPIN_DIR = os.path.join(ROOT, "oracle", "_ref", "dropin")
-DROPIN_SO = os.path.join(DROPIN_DIR, "libH265ToJpeg_b200.so")
+DROPIN_SO = os.path.join(ROOT, "h264-h265-to-jpeg_b200", "lib", "libH265ToJpeg_b200.so")
+FIXTURES = os.path.join(ROOT, "oracle", "_ref", "fixtures")  # the reference's test/img pictures (test infrastructure)
 G = os.path.join(ROOT, "tests", "golden")
 
 
@@ -42,7 +42,7 @@ def test_host_encoder_class_writes_the_oracle_bytes(orc, tmp_path):
 def test_dropin_library_on_the_reference_fixtures(orc, name, tmp_path):
     lib = C.CDLL(DROPIN_SO)
     lib.dropin_h265_to_jpeg.argtypes = [C.c_char_p, C.c_char_p]
-    src = os.path.join(DROPIN_DIR, "fixtures", name)
+    src = os.path.join(FIXTURES, name)
     out = str(tmp_path / (name + ".jpeg"))
     assert lib.dropin_h265_to_jpeg(src.encode(), out.encode()) == 1
     got = open(out, "rb").read()
@@ -101,7 +101,7 @@ def test_dropin_batch_scope_on_the_reference_fixtures(tmp_path):
     outs = []
     for i, name in enumerate(names):
         out = str(tmp_path / f"{i}_{name}.jpeg")
-        assert lib.dropin_h265_to_jpeg(os.path.join(DROPIN_DIR, "fixtures", name).encode(), out.encode()) == 1
+        assert lib.dropin_h265_to_jpeg(os.path.join(FIXTURES, name).encode(), out.encode()) == 1
         outs.append(out)
     failed = C.c_int(-1)
     assert lib.h2j_host_batch_end(C.byref(failed)) == len(names) and failed.value == 0

@@ -23,6 +23,7 @@ def test_1080p_batch_round_trip_and_position_independence(orc):
     order[63] = 0
     frames = np.stack([base[i] for i in order])
     d = torch.from_numpy(frames).cuda()
+    torch.cuda.synchronize()
     nblk = ((w + 15) // 16) * ((h + 15) // 16) * 6
     with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=n, n_slots=1) as e:
         e.submit_device(0, d.data_ptr(), frames.shape[1], n, w, h)

@@ -53,6 +53,7 @@ def test_nv12_matches_planar(orc, w, h, pitch_align, extra_rows, kind):
     for i, fr in enumerate(frames):
         host[i, : len(fr)] = fr
     d = torch.from_numpy(host).cuda()
+    torch.cuda.synchronize()
     with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=n, n_slots=1) as e:
         e.submit_device_nv12(0, d.data_ptr(), stride, pitch, uv_off, n, w, h)
         res = e.collect(0)
@@ -62,6 +63,11 @@ def test_nv12_matches_planar(orc, w, h, pitch_align, extra_rows, kind):
         # an unaligned base address takes the byte path and must give the same bytes
         d2 = torch.zeros(n * stride + 1, dtype=torch.uint8, device="cuda")
         d2[1:] = d.reshape(-1)
+        # d2 is produced on torch's current stream, the slot runs on its own: order the slot behind the producer
+        # (include/h2j_b200.h, "Stream ordering of device inputs")
+        ev = torch.cuda.Event()
+        ev.record()
+        e.wait_event(0, ev.cuda_event)
         e.submit_device_nv12(0, d2.data_ptr() + 1, stride, pitch, uv_off, n, w, h)
         res2 = e.collect(0)
         assert res2.jpegs == res.jpegs
@@ -78,6 +84,7 @@ def test_nv12_in_place_with_range_conversion_and_fixed_qscale(orc):
     y, u, v = orc.synth_planes(w, h, "textured", seed=77)
     fr = to_nv12(y, u, v, pitch, pitch * h)
     d = torch.from_numpy(fr).cuda()
+    torch.cuda.synchronize()
     for kw, okw in (({"range_mode": 1}, {"range_mode": 1}), ({"fixed_qscale": 3}, {"fixed_qscale": 3})):
         with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=1, n_slots=1, **kw) as e:
             e.submit_device_nv12(0, d.data_ptr(), len(fr), pitch, pitch * h, 1, w, h)

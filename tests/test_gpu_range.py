@@ -27,7 +27,9 @@ def _pad(p, pw, ph, uw, uh):
     return np.pad(q, ((0, ph - uh), (0, pw - uw)), mode="edge")
 
 
-@pytest.mark.parametrize("w,h", [(64, 48), (322, 242), (1918, 1078), (1920, 1080), (33, 17)])
+# 720x576 and 272x208: w = 16 (mod 32), so the chroma pitch w/2 = 8 (mod 16) and every odd chroma row starts 8 bytes off
+# a 16-byte boundary (the 128-bit load path must be chosen per row, not per frame)
+@pytest.mark.parametrize("w,h", [(64, 48), (322, 242), (1918, 1078), (1920, 1080), (33, 17), (720, 576), (272, 208), (848, 480)])
 def test_convert_pad_matches_swscale_and_edge_rule(orc, w, h):
     import h2j_b200
 
