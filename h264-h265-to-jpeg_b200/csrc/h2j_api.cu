@@ -30,7 +30,8 @@ struct Slot {
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
     uint8_t *d_frames = nullptr;  // staging for host submits
     uint8_t *d_pitched = nullptr; // copies of frames with unaligned rows at a 16-byte pitch (allocated on first need)
-    uint32_t *d_images = nullptr;  // [max_batch][images_cap] tile images (h2j_common.cuh)
+    uint32_t *d_images = nullptr;  // [max_batch][img_words_cap] compact coefficient regions (h2j_common.cuh)
+    uint2 *d_dir = nullptr;        // [max_batch][images_cap][kDirPerTile] where K2 put each (tile, role) sub-image
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
@@ -73,7 +74,8 @@ struct h2j_encoder {
     int sm_count = 0;
     size_t out_cap = 0;           // per-frame JPEG capacity (multiple of 16)
     long long scan_cap_words = 0;
-    long long images_cap = 0;     // K2 tile images per frame at max geometry, rounded up to whole K4 tiles
+    long long images_cap = 0;     // K2 tiles per frame at max geometry
+    long long img_words_cap = 0;  // words of a frame's coefficient region: every sub-image at its worst-case length
     long long blocks_cap = 0;     // images_cap * 96
     int tiles_cap = 0;            // K4 tiles per frame at max geometry
     int units_cap = 0;            // K4 units (32 blocks) per frame
@@ -301,8 +303,8 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
         const dim3 grid(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
-        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
-        else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap, tiles_per_cta);
+        else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap, tiles_per_cta);
         e->launches++;
     }
     {
@@ -311,11 +313,10 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
                                                                        e->d_comment, (int)e->comment.size());
         e->launches++;
     }
-    const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
         ScopedTiming t(e, sl, "entropy_walk_kernel");
-        entropy_walk_kernel<<<dim3(tiles_per_frame, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info,
-                                                                                         e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        entropy_walk_kernel<<<dim3(n_tiles, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap,
+                                                                                 sl.d_unit_info, e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
         e->launches++;
     }
     {
@@ -416,7 +417,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_pitched); cudaFree(sl.d_images); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
+    cudaFree(sl.d_frames); cudaFree(sl.d_pitched); cudaFree(sl.d_images); cudaFree(sl.d_dir); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -535,9 +536,10 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->scan_cap_words = (long long)(e->out_cap / 4);
     const int mcu_w = (s->max_width + 15) >> 4, mcu_h = (s->max_height + 15) >> 4;
     const long long n_mcu = (long long)mcu_w * mcu_h;
-    e->images_cap = ((n_mcu + kTileMcus - 1) / kTileMcus + kEntFdctTiles - 1) / kEntFdctTiles * kEntFdctTiles;
+    e->images_cap = (n_mcu + kTileMcus - 1) / kTileMcus;
+    e->img_words_cap = e->images_cap * kTileRoles * kSubMaxWords;
     e->blocks_cap = e->images_cap * kTileBlocks;
-    e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
+    e->tiles_cap = (int)e->images_cap;
     e->units_cap = e->tiles_cap * kEntWarps;
     e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
     // a fixed place of one window per unit, then the reserved area for units that need more (every unit starts on a word:
@@ -568,7 +570,8 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_begin));
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
-        CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
+        CUB(cudaMalloc(&sl.d_images, (size_t)e->img_words_cap * 4 * B + 16));  // (+16: K4a may read one word past a list)
+        CUB(cudaMalloc(&sl.d_dir, sizeof(uint2) * (size_t)e->images_cap * kDirPerTile * B));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
         const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->groups_cap * B, 256);
         const size_t alloc_bytes = align_up(sizeof(unsigned int) * (size_t)B, 256);
@@ -888,9 +891,9 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
     if (rc) return rc;
     CU(e, cudaMemcpyAsync(sl.d_frames, sl.h_stage, fb, cudaMemcpyHostToDevice, sl.stream));
     const int pw = L.mcu_w * 16, ph = L.mcu_h * 16;
-    // padded planes are produced in the (otherwise idle) coefficient buffer: 136 bytes per 64 samples, always enough
+    // padded planes are produced in the (otherwise idle) coefficient buffer: 256 bytes per 64 samples, always enough
     const size_t need = (size_t)pw * ph * 3 / 2;
-    if (need > (size_t)e->images_cap * kTileImageBytes * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's scratch buffer");
+    if (need > (size_t)e->img_words_cap * 4 * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's scratch buffer");
     uint8_t *oy = reinterpret_cast<uint8_t *>(sl.d_images), *ou = oy + (size_t)pw * ph, *ov = ou + (size_t)pw * ph / 4;
     convert_pad_kernel<<<dim3((pw / 16 + 127) / 128, ph, 3), 128, 0, sl.stream>>>(sl.d_frames, L, range_mode, oy, ou, ov);
     e->launches++;
@@ -940,19 +943,39 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     if (out_elems < need) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "need %zu int16 elements", need);
     ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
-    // tile images -> dense blocks; halfword 0 of a record is the DC difference, so the levels are rebuilt by
-    // running the encoder's predictors (one per component, reset to 128) over the blocks in coding order
+    // compact sub-images -> dense blocks.  The header holds the DC *difference*, so the levels are rebuilt by running the
+    // encoder's predictors (one per component, reset to 128) over the blocks in coding order; an entry's position is the
+    // previous non-zero position + run + 1.
     const int n_tiles = (sl.L.n_mcu + kTileMcus - 1) / kTileMcus;
-    std::vector<int16_t> img((size_t)n_tiles * kTileImageWords * 2);
-    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->images_cap * kTileImageWords, img.size() * sizeof(int16_t),
-                     cudaMemcpyDeviceToHost));
+    FrameState fs;
+    CU(e, cudaMemcpy(&fs, sl.d_state + frame, sizeof fs, cudaMemcpyDeviceToHost));
+    if ((long long)fs.img_words > e->img_words_cap) return fail(e, H2J_ERR_CUDA, "coefficient region overrun: %u words", fs.img_words);
+    std::vector<uint32_t> img((size_t)fs.img_words);
+    std::vector<uint2> dirv((size_t)n_tiles * kDirPerTile);
+    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->img_words_cap, img.size() * 4, cudaMemcpyDeviceToHost));
+    CU(e, cudaMemcpy(dirv.data(), sl.d_dir + (size_t)frame * e->images_cap * kDirPerTile, dirv.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
     int last_dc[3] = {128, 128, 128};
     for (int b = 0; b < sl.L.n_blocks; b++) {
-        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords + (size_t)tile_rec_word(b % kTileBlocks)) * 2;
+        const TileRec tr = tile_rec(b % kTileBlocks);
+        const uint2 d = dirv[(size_t)(b / kTileBlocks) * kDirPerTile + tr.sub];
+        if ((size_t)d.x + d.y > img.size() || d.y < (unsigned)kSubHdrWords) return fail(e, H2J_ERR_CUDA, "bad directory entry for block %d", b);
+        const uint32_t *sub = img.data() + d.x;
+        const uint32_t hdr = sub[tr.idx];
         const int n = b % 6, comp = n < 4 ? 0 : n - 3;
-        last_dc[comp] += rec[0];
-        out[(size_t)b * 64] = (int16_t)last_dc[comp];
-        for (int k = 1; k < 64; k++) out[(size_t)b * 64 + k] = rec[2 * (k & 31) + (k >> 5)];
+        int16_t *o = out + (size_t)b * 64;
+        memset(o, 0, 64 * sizeof(int16_t));
+        last_dc[comp] += sub_hdr_diff(hdr);
+        o[0] = (int16_t)last_dc[comp];
+        int pos = 0;
+        for (int i = 0; i < sub_hdr_count(hdr); i++) {
+            const unsigned at = (unsigned)kSubHdrWords + (unsigned)sub_hdr_first(hdr) + (unsigned)i;
+            if (at >= d.y) return fail(e, H2J_ERR_CUDA, "entry list of block %d leaves its sub-image", b);
+            const uint32_t en = sub[at];
+            pos += entry_run(en) + 1;
+            if (pos > 63) return fail(e, H2J_ERR_CUDA, "entry positions of block %d leave the block", b);
+            o[pos] = (int16_t)entry_level(en);
+        }
+        if ((pos < 63) != (sub_hdr_eob(hdr) != 0)) return fail(e, H2J_ERR_CUDA, "EOB flag of block %d contradicts its entries", b);
     }
     return H2J_OK;
 }

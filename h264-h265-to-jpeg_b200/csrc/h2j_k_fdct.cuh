@@ -16,8 +16,14 @@
 // output of ff_fdct_sse2 is exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17
 // == S), so eight lanes add one pixel row each -- no second FDCT.
 //
-// The tile image (h2j_common.cuh) is three sub-images, one per role.  A warp assembles its sub-image in one of its two
-// shared-memory buffers and sends it with its own bulk (TMA) store.
+// What leaves the kernel is the role's COMPACT sub-image of the tile (h2j_common.cuh): a header word per block and one
+// entry per non-zero AC level.  The quantised levels are first written to a scratch record per lane in shared memory
+// (registers cannot be indexed by a position found at run time); the statistics walk, which visits every non-zero level
+// anyway to count its (run, size) symbol, appends the level's entry -- level, run, size -- to the lane's list in the
+// staging buffer, at the offset a warp scan of the non-zero counts gave it.  The sub-image goes to the place a per-frame
+// bump allocator hands out with ONE bulk (TMA) store of exactly its length, and the (tile, role) directory entry
+// records where.  A tile whose lists outgrow the staging buffer (more than ~31 non-zero levels per block on average)
+// writes its entries straight to global memory instead.
 // Pixel rows of the next tile are requested before the statistics of the current one are taken, so their latency
 // is covered by work.
 //
@@ -187,14 +193,19 @@ __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const Plan
     return s;
 }
 
+constexpr int kFdctStageWords = 1024;  // staging buffer of a warp: 32 headers + up to 992 entries (4 KiB)
+
 template <bool NV12>
 __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
                                                                      FrameState *__restrict__ state,
                                                                      const FrameTab *__restrict__ tabs,
-                                                                     uint32_t *__restrict__ images,  // [frame][images_cap] tile images
+                                                                     uint32_t *__restrict__ images,  // [frame][img_words_cap] coefficient regions
+                                                                     long long img_words_cap,
+                                                                     uint2 *__restrict__ dir,        // [frame][images_cap][kDirPerTile] (offset, words)
                                                                      long long images_cap, int tiles_per_cta)
 {
-    __shared__ __align__(128) uint32_t s_img[2][kSubImageWords];
+    __shared__ __align__(128) uint32_t s_out[kFdctStageWords];
+    __shared__ uint32_t s_rec[kSubRecs * kBlkWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
     __shared__ unsigned int s_hist[256];
@@ -246,14 +257,10 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     __syncwarp();
 
     int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
+    uint32_t *gimg = images + (long long)f * img_words_cap;
 
     for (int tile = tile0; tile < tile_end; tile++) {
-        // this warp's sub-image of the tile, in one of its two buffers; the store that used this buffer two tiles ago must
-        // have read it out (lane 0 issued it, lane 0 waits)
-        uint32_t *img = s_img[(tile - tile0) & 1];
         const bool valid = bp.m < L.n_mcu;
-        if (lane == 0) bulk_wait_read_but_one();
-        __syncwarp();
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
         int psum = nvc ? fetch_pred_rowsum<true>(F, Q, pp, phelp_at(tile), lane & 7, lut) : fetch_pred_rowsum<false>(F, Q, pp, phelp_at(tile), lane & 7, lut);
@@ -269,9 +276,8 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         else pred_first = chroma_carry;
 
         unsigned mask_lo = 0, mask_hi = 0;
-        uint32_t word0_hi = 0;
         int dc = 0;
-        uint32_t *rec = img + lane * kBlkWords;  // the lane order of every warp is its record order
+        uint32_t *rec = s_rec + lane * kBlkWords;  // scratch record (this lane writes it, this lane reads it back)
         if (valid) {
             int v[64];
             if (nvc) fetch_consume<true>(F, R, bp, lut, v);
@@ -291,13 +297,10 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                 const unsigned t = __vminu2(w, 0x00010001u);
                 if (j < 16) fa += t << j;
                 else fb += t << (j - 16);
-                if (j == 0) word0_hi = w;  // the low half becomes the DC difference below
-                else rec[j] = w;
+                rec[j] = w;  // (word 0: low half unused, high half = level 32)
             }
             mask_lo = ((fa & 0xffffu) | (fb << 16)) & ~1u;  // bit 0 is the DC position: always coded, never in the mask
             mask_hi = (fa >> 16) | (fb & 0xffff0000u);
-            rec[kMaskLoWord] = mask_lo;
-            img[kSubMaskHiOff + lane] = mask_hi;
         }
 
         // ---- request the next tile's pixels: nothing of this tile's 64-value block is live any more ----
@@ -308,33 +311,60 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             else fetch_issue<false, false>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
+        // ---- where the lists go: a warp scan of the non-zero counts; the sub-image's place in the frame's region ----
+        const int cnt = __popc(mask_lo) + __popc(mask_hi);  // (0 for blocks that do not exist)
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int first = incl - cnt;
+        const int words = kSubHdrWords + __shfl_sync(0xffffffffu, incl, 31);
+        const int words16 = (words + 3) & ~3;  // allocation and bulk-copy granule: 16 bytes
+        const bool staged = words <= kFdctStageWords;  // (warp-uniform)
+        unsigned goff = 0;  // lane 0 (every lane of a tile that is not staged): the sub-image's first word in the region
+        if (lane == 0) goff = atomicAdd(&state[f].img_words, (unsigned)words16);
+        // the store of the previous tile must have read the staging buffer out (lane 0 issued it, lane 0 waits; it had a
+        // whole transform's time to do so)
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        uint32_t *sub;  // headers at sub[0..31], entries behind
+        if (staged) sub = s_out;
+        else {
+            goff = __shfl_sync(0xffffffffu, goff, 0);
+            sub = gimg + goff;
+        }
+        uint32_t *dst = sub + kSubHdrWords + first;
+
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
         const int up = __shfl_up_sync(0xffffffffu, dc, 1);
         const int pred = (luma ? lane == 0 : (lane & 15) == 0) ? pred_first : up;
         const int last = __shfl_sync(0xffffffffu, dc, (lane & 16) | 15);  // chroma: this tile's last Cb / Cr
         chroma_carry = last;
+        uint32_t hdr = 0;
         if (valid) {
             const int diff = dc - pred;
-            rec[0] = (uint32_t)(diff & 0xffff) | word0_hi;
             atomicAdd(&s_dchist[mag_bits(diff)], 1u);
-            // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
+            // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) and the block's entry list ----
             // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
-            // below it and its value, so the levels can be visited in any order.  Positions 1..31 (where nearly all of
-            // them are) are taken two at a time: two independent bit-scan -> load -> size -> atomic chains per
-            // iteration instead of one, half the trips.
+            // below it and its value.  Positions are taken in ascending order, two at a time: two independent
+            // bit-scan -> load -> size -> atomic chains per iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
             unsigned int *hist = s_hist;
             unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
             auto count = [&](int k, int below, int val) {  // val != 0
                 const int run = k - below - 1;
-                unsigned top;  // size - 1: the + 1 rides in the address (size <= 15, no carry into the run nibble)
+                unsigned top;  // size - 1
                 asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(val)));
                 zrl += (unsigned)run >> 4;
-                atomicAdd(&hist[1 + (((run & 15) << 4) | (int)top)], 1u);
+                // entry: level | run << 4 | size; its low byte is the symbol (run & 15) << 4 | size (size <= 11: no carry)
+                const unsigned e = ((unsigned)val << 16) | (unsigned)((run << 4) + (int)top + 1);
+                atomicAdd(&hist[e & 0xffu], 1u);
+                *dst++ = e;
             };
             unsigned lo = mask_lo;
             const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
-#if H2J_K2_WALK
             // H2J_K2_WALK positions per trip, taken from the low end, without a branch inside: the chains (position -> level
             // -> size -> histogram) are independent, the ones a lane does not have are predicated off
             int below = 0;
@@ -355,25 +385,6 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                 if (H2J_K2_WALK >= 4 && b3) count(k3, k2, (int)lv[2 * max(k3, 0)]);
                 below = 31 - __clz(b0 | b1 | b2 | b3);
             }
-#else
-            int below_a = 0;   // ascending end: the non-zero position below the next one taken
-            int kb = top_lo;   // descending end: the highest position still in `lo`
-            while (lo) {
-                const unsigned bit_a = lo & (0u - lo);
-                const int ka = 31 - __clz(bit_a);
-                lo ^= bit_a;
-                const int val_a = (int)lv[2 * ka];
-                if (lo) {  // ka was not the last one: kb is a different position
-                    lo ^= 1u << kb;
-                    const int val_b = (int)lv[2 * kb];
-                    const int below_b = lo ? 31 - __clz(lo) : ka;  // next one down, or the one the other end just took
-                    count(kb, below_b, val_b);
-                    kb = below_b;
-                }
-                count(ka, below_a, val_a);
-                below_a = ka;
-            }
-#endif
             int prev = top_lo;
             unsigned hi = mask_hi;
             while (hi) {
@@ -384,13 +395,17 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             }
             if (prev < 63) atomicAdd(&hist[0], 1u);
             if (zrl) atomicAdd(&hist[0xf0], zrl);
+            hdr = sub_hdr_pack(diff, prev < 63 ? 1 : 0, cnt, first);
         }
+        sub[lane] = hdr;
 
-        // ---- the warp's sub-image leaves with one bulk store ----
-        fence_proxy_async_smem();
+        // ---- the warp's sub-image leaves with one bulk store of its own length; the directory says where it went ----
+        if (staged) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0)
-            bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords + warp * kSubImageWords, img, kSubImageBytes);
+        if (lane == 0) {
+            if (staged) bulk_s2g(gimg + goff, s_out, (uint32_t)words16 * 4u);
+            dir[((long long)f * images_cap + tile) * kDirPerTile + warp] = make_uint2(goff, (unsigned)words);
+        }
     }
     // the stores only have to be done READING shared memory before the CTA retires; they complete on their own and the
     // kernel boundary orders them before K4a
