@@ -31,7 +31,7 @@ struct Slot {
     uint8_t *d_frames = nullptr;  // staging for host submits
     uint8_t *d_pitched = nullptr; // copies of frames with unaligned rows at a 16-byte pitch (allocated on first need)
     uint32_t *d_images = nullptr;  // [max_batch][img_words_cap] compact coefficient regions (h2j_common.cuh)
-    uint2 *d_dir = nullptr;        // [max_batch][images_cap][kDirPerTile] where K2 put each (tile, role) sub-image
+    unsigned *d_dir = nullptr;     // [max_batch][images_cap][kDirPerTile] words of each (tile, role) sub-image
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
@@ -544,7 +544,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
     // a fixed place of one window per unit, then the reserved area for units that need more (every unit starts on a word:
     // at most one word of slack each)
-    e->stage_cap_words = (long long)e->units_cap * kWarpWinWords + e->scan_cap_words + e->units_cap;
+    e->stage_cap_words = ((long long)e->units_cap * kWarpWinWords + e->scan_cap_words + e->units_cap + 3) / 4 * 4;  // (frames' areas stay 16-byte aligned)
     e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
     e->frame_bytes_cap = std::max(align_up(tight_frame_bytes(s->max_width, s->max_height), 256), pitched_frame_bytes(s->max_width, s->max_height));
 
@@ -571,7 +571,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
         CUB(cudaMalloc(&sl.d_images, (size_t)e->img_words_cap * 4 * B + 16));  // (+16: K4a may read one word past a list)
-        CUB(cudaMalloc(&sl.d_dir, sizeof(uint2) * (size_t)e->images_cap * kDirPerTile * B));
+        CUB(cudaMalloc(&sl.d_dir, sizeof(unsigned) * (size_t)e->images_cap * kDirPerTile * B));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
         const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->groups_cap * B, 256);
         const size_t alloc_bytes = align_up(sizeof(unsigned int) * (size_t)B, 256);
@@ -947,19 +947,16 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     // encoder's predictors (one per component, reset to 128) over the blocks in coding order; an entry's position is the
     // previous non-zero position + run + 1.
     const int n_tiles = (sl.L.n_mcu + kTileMcus - 1) / kTileMcus;
-    FrameState fs;
-    CU(e, cudaMemcpy(&fs, sl.d_state + frame, sizeof fs, cudaMemcpyDeviceToHost));
-    if ((long long)fs.img_words > e->img_words_cap) return fail(e, H2J_ERR_CUDA, "coefficient region overrun: %u words", fs.img_words);
-    std::vector<uint32_t> img((size_t)fs.img_words);
-    std::vector<uint2> dirv((size_t)n_tiles * kDirPerTile);
+    std::vector<uint32_t> img((size_t)n_tiles * kTileRoles * kSubMaxWords);
+    std::vector<unsigned> dirv((size_t)n_tiles * kDirPerTile);
     CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->img_words_cap, img.size() * 4, cudaMemcpyDeviceToHost));
-    CU(e, cudaMemcpy(dirv.data(), sl.d_dir + (size_t)frame * e->images_cap * kDirPerTile, dirv.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+    CU(e, cudaMemcpy(dirv.data(), sl.d_dir + (size_t)frame * e->images_cap * kDirPerTile, dirv.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
     int last_dc[3] = {128, 128, 128};
     for (int b = 0; b < sl.L.n_blocks; b++) {
         const TileRec tr = tile_rec(b % kTileBlocks);
-        const uint2 d = dirv[(size_t)(b / kTileBlocks) * kDirPerTile + tr.sub];
-        if ((size_t)d.x + d.y > img.size() || d.y < (unsigned)kSubHdrWords) return fail(e, H2J_ERR_CUDA, "bad directory entry for block %d", b);
-        const uint32_t *sub = img.data() + d.x;
+        const unsigned sub_words = dirv[(size_t)(b / kTileBlocks) * kDirPerTile + tr.sub];
+        if (sub_words > (unsigned)kSubMaxWords || sub_words < (unsigned)kSubHdrWords) return fail(e, H2J_ERR_CUDA, "bad directory entry for block %d", b);
+        const uint32_t *sub = img.data() + ((size_t)(b / kTileBlocks) * kTileRoles + tr.sub) * kSubMaxWords;
         const uint32_t hdr = sub[tr.idx];
         const int n = b % 6, comp = n < 4 ? 0 : n - 3;
         int16_t *o = out + (size_t)b * 64;
@@ -969,7 +966,7 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
         int pos = 0;
         for (int i = 0; i < sub_hdr_count(hdr); i++) {
             const unsigned at = (unsigned)kSubHdrWords + (unsigned)sub_hdr_first(hdr) + (unsigned)i;
-            if (at >= d.y) return fail(e, H2J_ERR_CUDA, "entry list of block %d leaves its sub-image", b);
+            if (at >= sub_words) return fail(e, H2J_ERR_CUDA, "entry list of block %d leaves its sub-image", b);
             const uint32_t en = sub[at];
             pos += entry_run(en) + 1;
             if (pos > 63) return fail(e, H2J_ERR_CUDA, "entry positions of block %d leave the block", b);

@@ -49,17 +49,17 @@ struct FrameLayout {
 //   words 32..    entries, the blocks' lists back to back in record order, one per non-zero AC level in zigzag order:
 //                   [31:16] level (signed)
 //                   [9:4]   run of zeros in front of it (0..62): [9:8] ZRL symbols to emit first, [7:4] the symbol's run nibble
-//                   [3:0]   magnitude category (1..11) -- so [7:0] is the level's Huffman symbol
-// K4a never looks at positions or masks: it maps entry -> code and appends.  A sub-image is placed by a per-frame bump
-// allocator (FrameState::img_words, units of 4 words = 16 bytes: the granule of the bulk copies that move it) inside the
-// frame's region of `img_words_cap` words; the directory entry of (tile, role) says where it went and how long it is.
+//                   [3:0]   magnitude category - 1 (0..10) -- so [7:0] + 1 is the level's Huffman symbol
+// K4a never looks at positions or masks: it maps entry -> code and appends.  Sub-image (tile, role) of a frame starts at
+// word (tile * 3 + role) * kSubMaxWords of the frame's region (room for its densest form; only the words in use are ever
+// written or read -- in 16-byte granules, what the bulk copies move); the directory holds its length in words.
 constexpr int kTileMcus = 16;
 constexpr int kTileBlocks = kTileMcus * 6;                  // 96
 constexpr int kSubRecs = 32;
 constexpr int kSubHdrWords = kSubRecs;                      // 32
 constexpr int kSubMaxWords = kSubHdrWords + kSubRecs * 63;  // 2048: every AC level of every block non-zero
 constexpr int kTileRoles = 3;
-constexpr int kDirPerTile = 4;                              // directory entries per tile (three used): 32 bytes, one line
+constexpr int kDirPerTile = 4;                              // directory words per tile (three used): 16 bytes, one vector load
 __host__ __device__ inline uint32_t sub_hdr_pack(int dc_diff, int eob, int count, int first) { return ((uint32_t)dc_diff << 20) | ((uint32_t)eob << 19) | ((uint32_t)count << 12) | (uint32_t)first; }
 __host__ __device__ inline int sub_hdr_diff(uint32_t h) { return (int)h >> 20; }
 __host__ __device__ inline int sub_hdr_eob(uint32_t h) { return (int)((h >> 19) & 1u); }
@@ -97,7 +97,8 @@ struct alignas(16) FrameTab {
     uint32_t qpack[64];      // raster order: q | (bias*q) << 16   (inspection)
     uint8_t dqt_zz[64];      // DQT payload (zigzag order)
     uint8_t intra[64];       // raster order (inspection)
-    uint32_t hcode[4][256];  // (code << 5) | size; classes: 0 DC luma, 1 DC chroma, 2 AC luma, 3 AC chroma
+    uint32_t hcode[4][256];  // ((code << nb) << 5) | (code length + nb), nb = symbol & 15: the mantissa bits K4a appends;
+                             // classes: 0 DC luma, 1 DC chroma, 2 AC luma, 3 AC chroma
                              // (16-byte aligned inside the struct: K4 fetches the four tables with one bulk copy)
     uint8_t bits[4][17];
     uint8_t vals[4][256];
@@ -118,8 +119,7 @@ struct FrameState {
     unsigned long long scan_bits;   // written by the frame's last K4b group
     unsigned int k1_done;           // K1 CTAs that have added their share of var_sum
     unsigned int k3_done;           // K3 CTAs (one per table) that have finished: the fourth writes the header
-    unsigned int img_words;         // K2: words of the frame's coefficient region handed out so far (bump allocator)
-    unsigned int pad_;
+    unsigned int pad_[2];
     unsigned int hist[4][256];      // DC luma, DC chroma, AC luma, AC chroma symbol counts (K2)
 };
 

@@ -151,23 +151,23 @@ __device__ __forceinline__ void walk_block(const uint32_t *__restrict__ list, ui
     {
         const int diff = sub_hdr_diff(hdr);
         const int nb = mag_bits(diff);
-        const uint32_t e = hdc[nb];
+        const uint32_t e = hdc[nb];  // code tables come pre-shifted from K3: (code << nb) << 5 | (code length + nb)
         const unsigned mant = (unsigned)(diff + (diff >> 31)) & ((1u << nb) - 1u);
-        sink->put(((e >> 5) << nb) | mant, (int)(e & 31) + nb);
+        sink->put((e >> 5) | mant, (int)(e & 31));
     }
     const uint32_t zrl = hac[0xf0];
     auto code_one = [&](uint32_t en, uint32_t h) {
         if (en & 0x300u)
             for (int z = (int)((en >> 8) & 3u); z > 0; z--) sink->put(zrl >> 5, (int)(zrl & 31));
-        const int nb = (int)(en & 15u), lvl = entry_level(en);
+        const int nb = (int)(en & 15u) + 1, lvl = entry_level(en);
         const unsigned mant = (unsigned)(lvl + (lvl >> 31)) & ((1u << nb) - 1u);
-        sink->put(((h >> 5) << nb) | mant, (int)(h & 31) + nb);
+        sink->put((h >> 5) | mant, (int)(h & 31));
     };
     const int cnt = sub_hdr_count(hdr);
     for (int i = 0; i < cnt; i += 2) {
         const uint32_t e0 = list[i];
         const uint32_t e1 = list[i + 1];  // (one word past the list at the most: inside the image / the region's slack)
-        const uint32_t h0 = hac[e0 & 0xffu], h1 = hac[e1 & 0xffu];
+        const uint32_t h0 = hac[1 + (e0 & 0xffu)], h1 = hac[1 + (e1 & 0xffu)];  // (entry: size - 1; the + 1 rides in the address)
         code_one(e0, h0);
         if (i + 1 < cnt) code_one(e1, h1);
     }
@@ -189,7 +189,7 @@ static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0,
 // grid (tiles_per_frame, frames)
 __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L, FrameTab *__restrict__ tabs,
                                                                    const uint32_t *__restrict__ images, long long img_words_cap,
-                                                                   const uint2 *__restrict__ dir, long long images_cap,
+                                                                   const unsigned *__restrict__ dir, long long images_cap,
                                                                    unsigned long long *__restrict__ unit_info, int units_cap,
                                                                    unsigned int *__restrict__ stage_alloc,  // [frame] words handed out
                                                                    uint32_t *__restrict__ stage, long long stage_cap_words)
@@ -201,8 +201,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     unsigned int *s_win_all = s_hac + 512;                                               // [warp][kWarpWinStride]
     unsigned int *s_slot_all = s_win_all + kEntWarps * kWarpWinStride;                   // [warp][lane][kSlotStride]
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ unsigned s_sub_src[kTileRoles];   // first word of the role's sub-image in the frame's region
-    __shared__ unsigned s_sub_at[kTileRoles];    // ... and in s_img
+    __shared__ unsigned s_sub_at[kTileRoles];    // first word of the role's sub-image in s_img
     __shared__ int s_in_smem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,20 +209,17 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     const uint32_t *gimg = images + (long long)f * img_words_cap;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
-        // (offset, words) of the tile's three sub-images: one 32-byte directory line
-        const uint4 *D = reinterpret_cast<const uint4 *>(dir + ((long long)f * images_cap + tile) * kDirPerTile);
-        const uint4 d01 = __ldg(D), d2x = __ldg(D + 1);
-        const unsigned off[kTileRoles] = {d01.x, d01.z, d2x.x};
-        const unsigned w16[kTileRoles] = {(d01.y + 3u) & ~3u, (d01.w + 3u) & ~3u, (d2x.y + 3u) & ~3u};  // what K2 allocated and copied
+        // words of the tile's three sub-images: one 16-byte directory line
+        const uint4 d = __ldg(reinterpret_cast<const uint4 *>(dir + ((long long)f * images_cap + tile) * kDirPerTile));
+        const unsigned w16[kTileRoles] = {(d.x + 3u) & ~3u, (d.y + 3u) & ~3u, (d.z + 3u) & ~3u};  // what K2 copied out
         const unsigned total = w16[0] + w16[1] + w16[2];
         const bool in_smem = total <= (unsigned)kEntImgWords;
         mbar_expect_tx(&s_bar, (in_smem ? total * 4u : 0u) + kEntTabBytes);
         unsigned at = 0;
 #pragma unroll
         for (int r = 0; r < kTileRoles; r++) {
-            s_sub_src[r] = off[r];
             s_sub_at[r] = at;
-            if (in_smem) bulk_g2s(s_img + at, gimg + off[r], w16[r] * 4u, &s_bar);
+            if (in_smem) bulk_g2s(s_img + at, gimg + ((long long)tile * kTileRoles + r) * kSubMaxWords, w16[r] * 4u, &s_bar);
             at += w16[r];
         }
         s_in_smem = in_smem ? 1 : 0;
@@ -235,10 +231,11 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         const long long lin = (long long)f * gridDim.x + tile + kEntPrefetchDistance;
         if (lin < (long long)gridDim.x * gridDim.y) {
             const long long f2 = lin / gridDim.x, t2 = lin - f2 * gridDim.x;
-            bulk_prefetch_l2(dir + (f2 * images_cap + t2) * kDirPerTile, 32);
+            bulk_prefetch_l2(dir + (f2 * images_cap + t2) * kDirPerTile, 16);
         }
     }
-    for (int i = tid; i < kEntWarps * kWarpWinStride; i += kEntThreads) s_win_all[i] = 0;  // while the copies are on their way
+    static_assert((kEntWarps * kWarpWinStride) % 4 == 0 && ((kEntImgWords + 4) * 4 + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
+    for (int i = tid; i < kEntWarps * kWarpWinStride / 4; i += kEntThreads) reinterpret_cast<uint4 *>(s_win_all)[i] = make_uint4(0, 0, 0, 0);  // while the copies are on their way
     __syncthreads();  // barrier initialised, windows cleared, directory known
 
     // ---- from here on the warp is on its own ----
@@ -255,7 +252,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     const bool in_smem = s_in_smem != 0;                    // (CTA-uniform)
     // the sub-image this lane's block lives in: in shared memory, or (dense tile) where K2 put it
     const uint32_t *sub_s = s_img + s_sub_at[tr.sub];
-    const uint32_t *sub_g = gimg + s_sub_src[tr.sub];
+    const uint32_t *sub_g = gimg + ((long long)tile * kTileRoles + tr.sub) * kSubMaxWords;
 
     mbar_wait(&s_bar, 0);  // sub-images and code tables landed
     uint32_t hdr = 0;
@@ -326,7 +323,11 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         // ---- 3b. stage ----
         const unsigned pos = (unsigned)u * kWarpWinWords;
         if (lane == 0) unit_info[(long long)f * units_cap + u] = unit_pack(pos, unit_len);
-        for (unsigned i = lane; i < nwords; i += 32) st[pos + i] = win[i];
+        // (16 bytes per lane; the unit's fixed place and the window are 16-byte aligned, the words behind nwords up to the next
+        // multiple of four are zeros inside the unit's own place)
+        uint4 *dst4 = reinterpret_cast<uint4 *>(st + pos);
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(win);
+        for (unsigned i = lane; i * 4 < nwords; i += 32) dst4[i] = src4[i];
     } else {
         unsigned pos;
         const unsigned n_fit = claim(lane == 0 ? fixed_words + atomicAdd(&stage_alloc[f], nwords) : 0u, pos);

@@ -20,10 +20,10 @@
 // entry per non-zero AC level.  The quantised levels are first written to a scratch record per lane in shared memory
 // (registers cannot be indexed by a position found at run time); the statistics walk, which visits every non-zero level
 // anyway to count its (run, size) symbol, appends the level's entry -- level, run, size -- to the lane's list in the
-// staging buffer, at the offset a warp scan of the non-zero counts gave it.  The sub-image goes to the place a per-frame
-// bump allocator hands out with ONE bulk (TMA) store of exactly its length, and the (tile, role) directory entry
-// records where.  A tile whose lists outgrow the staging buffer (more than ~31 non-zero levels per block on average)
-// writes its entries straight to global memory instead.
+// staging buffer, at the offset a warp scan of the non-zero counts gave it.  The sub-image goes to the place its
+// (tile, role) owns in the frame's region with ONE bulk (TMA) store of exactly its length, and the (tile, role) directory
+// entry records that length.  A sub-image whose lists outgrow the staging buffer (more than 30 non-zero levels per block on
+// average) leaves in two pieces, sixteen blocks each.
 // Pixel rows of the next tile are requested before the statistics of the current one are taken, so their latency
 // is covered by work.
 //
@@ -31,10 +31,8 @@
 #pragma once
 #include "h2j_common.cuh"
 
-#ifndef H2J_K2_WALK
-#define H2J_K2_WALK 2  // positions the statistics walk takes per trip from the low end (0: the two-ended walk).  K2 per 2048 frames:
-                      // two-ended 5.538 ms, 2 per trip 5.511, 3 per trip 5.592, 4 per trip 5.626 (absent positions are predicated off)
-#endif
+// (the walk takes two positions per trip from the low end.  K2 per 2048 frames, r1: two-ended 5.538 ms, 2 per trip 5.511,
+// 3 per trip 5.592, 4 per trip 5.626 -- absent positions are predicated off)
 #ifndef H2J_FDCT_MIN_CTAS
 #define H2J_FDCT_MIN_CTAS 16  // resident single-warp CTAs per SM the register allocation is bounded for (16 -> 128 registers)
 #endif
@@ -193,7 +191,9 @@ __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const Plan
     return s;
 }
 
-constexpr int kFdctStageWords = 1024;  // staging buffer of a warp: 32 headers + up to 992 entries (4 KiB)
+constexpr int kFdctStageWords = 1088;  // staging buffer of a warp: 32 headers + up to 1056 entries (4.25 KiB); half a sub-image
+                                       // at its densest (16 blocks x 63 entries + the headers) always fits
+static_assert(kSubHdrWords + 16 * 63 <= kFdctStageWords, "half a sub-image must fit the staging buffer");
 
 template <bool NV12>
 __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                                                                      const FrameTab *__restrict__ tabs,
                                                                      uint32_t *__restrict__ images,  // [frame][img_words_cap] coefficient regions
                                                                      long long img_words_cap,
-                                                                     uint2 *__restrict__ dir,        // [frame][images_cap][kDirPerTile] (offset, words)
+                                                                     unsigned *__restrict__ dir,     // [frame][images_cap][kDirPerTile] words of each sub-image
                                                                      long long images_cap, int tiles_per_cta)
 {
     __shared__ __align__(128) uint32_t s_out[kFdctStageWords];
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             else fetch_issue<false, false>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
-        // ---- where the lists go: a warp scan of the non-zero counts; the sub-image's place in the frame's region ----
+        // ---- where the lists go: a warp scan of the non-zero counts ----
         const int cnt = __popc(mask_lo) + __popc(mask_hi);  // (0 for blocks that do not exist)
         int incl = cnt;
 #pragma unroll
@@ -319,93 +319,114 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        const int first = incl - cnt;
-        const int words = kSubHdrWords + __shfl_sync(0xffffffffu, incl, 31);
-        const int words16 = (words + 3) & ~3;  // allocation and bulk-copy granule: 16 bytes
-        const bool staged = words <= kFdctStageWords;  // (warp-uniform)
-        unsigned goff = 0;  // lane 0 (every lane of a tile that is not staged): the sub-image's first word in the region
-        if (lane == 0) goff = atomicAdd(&state[f].img_words, (unsigned)words16);
-        // the store of the previous tile must have read the staging buffer out (lane 0 issued it, lane 0 waits; it had a
-        // whole transform's time to do so)
-        if (lane == 0) bulk_wait_read_all();
-        __syncwarp();
-        uint32_t *sub;  // headers at sub[0..31], entries behind
-        if (staged) sub = s_out;
-        else {
-            goff = __shfl_sync(0xffffffffu, goff, 0);
-            sub = gimg + goff;
-        }
-        uint32_t *dst = sub + kSubHdrWords + first;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        // the (tile, role)'s own place in the frame's region.  (A bump allocator -- one atomicAdd per sub-image, for densely
+        // packed regions -- measured slower: all warps working on a frame queue up on one address, and lane 0 then waits for
+        // the answer when it issues the store: 5 % of the kernel's stall samples.)
+        uint32_t *gsub = gimg + ((long long)tile * kTileRoles + warp) * kSubMaxWords;
 
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
         const int up = __shfl_up_sync(0xffffffffu, dc, 1);
         const int pred = (luma ? lane == 0 : (lane & 15) == 0) ? pred_first : up;
         const int last = __shfl_sync(0xffffffffu, dc, (lane & 16) | 15);  // chroma: this tile's last Cb / Cr
         chroma_carry = last;
-        uint32_t hdr = 0;
+        const int diff = dc - pred;
         if (valid) {
-            const int diff = dc - pred;
             atomicAdd(&s_dchist[mag_bits(diff)], 1u);
-            // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) and the block's entry list ----
-            // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
-            // below it and its value.  Positions are taken in ascending order, two at a time: two independent
-            // bit-scan -> load -> size -> atomic chains per iteration instead of one, half the trips.
+            if (!(mask_hi >> 31)) atomicAdd(&s_hist[0], 1u);  // position 63 is zero: the block ends with an EOB
+        }
+
+        // The block's entry list (ff_mjpeg_encode_coef / record_block, AC part): one entry per non-zero level.  The
+        // (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level below it and
+        // its value.  Positions are taken in ascending order, two at a time: two independent bit-scan -> load -> size
+        // chains per iteration instead of one, half the trips.
+        auto walk_into = [&](uint32_t *dst) {
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
-            unsigned int *hist = s_hist;
-            unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
-            auto count = [&](int k, int below, int val) {  // val != 0
+            uint32_t *dst_hi = dst + __popc(mask_lo);
+            auto put = [&](uint32_t *at, int k, int below, int val) {  // val != 0
                 const int run = k - below - 1;
                 unsigned top;  // size - 1
                 asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(val)));
-                zrl += (unsigned)run >> 4;
-                // entry: level | run << 4 | size; its low byte is the symbol (run & 15) << 4 | size (size <= 11: no carry)
-                const unsigned e = ((unsigned)val << 16) | (unsigned)((run << 4) + (int)top + 1);
-                atomicAdd(&hist[e & 0xffu], 1u);
-                *dst++ = e;
+                *at = ((unsigned)val << 16) | (unsigned)((run << 4) + (int)top);  // entry: level | run << 4 | (size - 1)
             };
             unsigned lo = mask_lo;
-            const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
-            // H2J_K2_WALK positions per trip, taken from the low end, without a branch inside: the chains (position -> level
-            // -> size -> histogram) are independent, the ones a lane does not have are predicated off
             int below = 0;
             while (lo) {
                 const unsigned b0 = lo & (0u - lo);
                 lo ^= b0;
                 const unsigned b1 = lo & (0u - lo);
                 lo ^= b1;
-                const unsigned b2 = H2J_K2_WALK >= 3 ? lo & (0u - lo) : 0u;
-                lo ^= b2;
-                const unsigned b3 = H2J_K2_WALK >= 4 ? lo & (0u - lo) : 0u;
-                lo ^= b3;
-                const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1), k2 = 31 - __clz(b2), k3 = 31 - __clz(b3);  // -1: absent
+                const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1);  // k1 = -1: absent (then this was the last trip)
                 const int v0 = (int)lv[2 * k0], v1 = (int)lv[2 * max(k1, 0)];
-                count(k0, below, v0);
-                if (b1) count(k1, k0, v1);
-                if (H2J_K2_WALK >= 3 && b2) count(k2, k1, (int)lv[2 * max(k2, 0)]);
-                if (H2J_K2_WALK >= 4 && b3) count(k3, k2, (int)lv[2 * max(k3, 0)]);
-                below = 31 - __clz(b0 | b1 | b2 | b3);
+                put(dst, k0, below, v0);
+                if (b1) put(dst + 1, k1, k0, v1);
+                dst += 2;
+                below = k1;
             }
-            int prev = top_lo;
+            int prev = mask_lo ? 31 - __clz(mask_lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
             unsigned hi = mask_hi;
             while (hi) {
                 const int bp = __ffs((int)hi) - 1, k = 32 + bp;
                 hi &= hi - 1;
-                count(k, prev, (int)lv[2 * bp + 1]);
+                put(dst_hi++, k, prev, (int)lv[2 * bp + 1]);
                 prev = k;
             }
-            if (prev < 63) atomicAdd(&hist[0], 1u);
-            if (zrl) atomicAdd(&hist[0xf0], zrl);
-            hdr = sub_hdr_pack(diff, prev < 63 ? 1 : 0, cnt, first);
-        }
-        sub[lane] = hdr;
+        };
+        // Symbol statistics of finished lists, a lane per entry (every lane busy, unlike in the walk): (run & 15, size)
+        // counts and 16-zero runs (symbol 0xF0)
+        auto count_entries = [&](int e0, int e1) {
+#pragma unroll 1
+            for (int i = e0 + lane; i < e1; i += 32) {
+                const unsigned e = s_out[i];
+                atomicAdd(&s_hist[1 + (e & 0xffu)], 1u);  // (the symbol's size nibble is the entry's + 1: rides in the address)
+                if (e & 0x300u) atomicAdd(&s_hist[0xf0], (e >> 8) & 3u);  // runs of 16 and more are rare
+            }
+        };
 
-        // ---- the warp's sub-image leaves with one bulk store of its own length; the directory says where it went ----
-        if (staged) fence_proxy_async_smem();
+        // the store of the previous tile must have read the staging buffer out (lane 0 issued it, lane 0 waits; it had a
+        // whole transform's time to do so)
+        if (lane == 0) bulk_wait_read_all();
         __syncwarp();
-        if (lane == 0) {
-            if (staged) bulk_s2g(gimg + goff, s_out, (uint32_t)words16 * 4u);
-            dir[((long long)f * images_cap + tile) * kDirPerTile + warp] = make_uint2(goff, (unsigned)words);
+        int words;
+        if (kSubHdrWords + total <= kFdctStageWords) {
+            // ---- the usual case: the whole sub-image is assembled in the staging buffer and leaves with one bulk store ----
+            const int first = incl - cnt;
+            // header: everything in it is known before the walk (an EOB is coded unless position 63 is non-zero)
+            s_out[lane] = valid ? sub_hdr_pack(diff, (int)(~mask_hi >> 31), cnt, first) : 0u;
+            if (valid) walk_into(s_out + kSubHdrWords + first);
+            __syncwarp();
+            count_entries(kSubHdrWords, kSubHdrWords + total);
+            words = kSubHdrWords + total;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_s2g(gsub, s_out, (uint32_t)((words + 3) & ~3) * 4u);
+        } else {
+            // ---- dense content (more than 30 non-zero levels per block on average): two pieces, lanes 0-15 (with the
+            //      headers), then lanes 16-31, whose lists start on the next 16-byte boundary (the bulk copy's granule);
+            //      half a sub-image always fits the buffer ----
+            const int half_a = __shfl_sync(0xffffffffu, incl, 15);  // entries of lanes 0-15
+            const int split = (half_a + 3) & ~3;                    // where the second piece's entries start
+            const int first = incl - cnt + (lane >= 16 ? split - half_a : 0);
+            s_out[lane] = valid ? sub_hdr_pack(diff, (int)(~mask_hi >> 31), cnt, first) : 0u;
+            if (valid && lane < 16) walk_into(s_out + kSubHdrWords + first);
+            __syncwarp();
+            count_entries(kSubHdrWords, kSubHdrWords + half_a);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(gsub, s_out, (uint32_t)(kSubHdrWords + split) * 4u);
+                bulk_wait_read_all();  // the second piece reuses the buffer
+            }
+            __syncwarp();
+            if (valid && lane >= 16) walk_into(s_out + (first - split));
+            __syncwarp();
+            count_entries(0, total - half_a);
+            words = kSubHdrWords + split + (total - half_a);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_s2g(gsub + kSubHdrWords + split, s_out, (uint32_t)((total - half_a + 3) & ~3) * 4u);
         }
+        if (lane == 0) dir[((long long)f * images_cap + tile) * kDirPerTile + warp] = (unsigned)words;
     }
     // the stores only have to be done READING shared memory before the CTA retires; they complete on their own and the
     // kernel boundary orders them before K4a

@@ -277,7 +277,10 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
     for (int i = gt; i < nval; i += kHuffGroup) {
         const int len = S->distinct[i].b;
         const int code = S->first_code[len] + (i - S->first_index[len]);
-        g_hcode[S->distinct[i].a] = ((uint32_t)code << 5) | (uint32_t)len;
+        // K4a appends nb mantissa bits behind the code of a symbol whose low nibble is nb (DC: the symbol itself), so the
+        // table holds the code already shifted into place and the total length: (code << nb) << 5 | (len + nb)
+        const int sym = S->distinct[i].a, nb = sym & 15;
+        g_hcode[sym] = (((uint32_t)code << nb) << 5) | (uint32_t)(len + nb);
     }
     K3_STAMP(6);
 }
