@@ -4,12 +4,16 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "h2j_kernels.cuh"
@@ -30,8 +34,7 @@ struct Slot {
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
     uint8_t *d_frames = nullptr;  // staging for host submits
     uint8_t *d_pitched = nullptr; // copies of frames with unaligned rows at a 16-byte pitch (allocated on first need)
-    uint32_t *d_images = nullptr;  // [max_batch][img_words_cap] compact coefficient regions (h2j_common.cuh)
-    unsigned *d_dir = nullptr;     // [max_batch][images_cap][kDirPerTile] words of each (tile, role) sub-image
+    uint32_t *d_images = nullptr;  // [max_batch][images_cap] tile images (h2j_common.cuh)
     uint8_t *d_zero = nullptr;    // FrameState[max_batch] | descs | ticket | chunk_ff — zeroed every batch
     size_t zero_bytes = 0;
     FrameState *d_state = nullptr;
@@ -74,8 +77,7 @@ struct h2j_encoder {
     int sm_count = 0;
     size_t out_cap = 0;           // per-frame JPEG capacity (multiple of 16)
     long long scan_cap_words = 0;
-    long long images_cap = 0;     // K2 tiles per frame at max geometry
-    long long img_words_cap = 0;  // words of a frame's coefficient region: every sub-image at its worst-case length
+    long long images_cap = 0;     // K2 tile images per frame at max geometry, rounded up to whole K4 tiles
     long long blocks_cap = 0;     // images_cap * 96
     int tiles_cap = 0;            // K4 tiles per frame at max geometry
     int units_cap = 0;            // K4 units (32 blocks) per frame
@@ -303,8 +305,8 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
         const dim3 grid(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
-        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap, tiles_per_cta);
-        else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap, tiles_per_cta);
+        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }
     {
@@ -313,10 +315,11 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
                                                                        e->d_comment, (int)e->comment.size());
         e->launches++;
     }
+    const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
         ScopedTiming t(e, sl, "entropy_walk_kernel");
-        entropy_walk_kernel<<<dim3(n_tiles, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->img_words_cap, sl.d_dir, e->images_cap,
-                                                                                 sl.d_unit_info, e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        entropy_walk_kernel<<<dim3(tiles_per_frame, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info,
+                                                                                         e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
         e->launches++;
     }
     {
@@ -407,6 +410,129 @@ struct DeviceGuard {
     DeviceGuard device_guard__((e)->s.device); \
     CU(e, device_guard__.err)
 
+// ---- staging copies of h2j_encode_frame, spread over a few host threads -----------------------------------------
+// One picture's planes go from the caller's (pageable) memory into pinned staging before they can be uploaded; a single
+// thread copies about 10 GB/s, which made that memcpy -- 0.3 ms for a 1080p frame -- three quarters of the whole call.
+// The copy is cut into pieces; the caller and up to three helper threads take pieces off a shared counter, and the
+// caller uploads every piece as soon as it and all pieces in front of it are in place.  The helpers are process-wide,
+// start with the first picture and sleep between pictures (after a short spin, so that back-to-back calls find them awake).
+struct CopyPiece {
+    uint8_t *dst;
+    const uint8_t *src;
+    int rows, row_bytes, dst_pitch, src_stride;
+    size_t dev_off, dev_bytes;  // where the piece goes in the slot's frame buffer
+};
+
+void copy_piece(const CopyPiece &c)
+{
+    if (c.src_stride == c.row_bytes && c.dst_pitch == c.row_bytes) memcpy(c.dst, c.src, (size_t)c.rows * c.row_bytes);
+    else
+        for (int r = 0; r < c.rows; r++) memcpy(c.dst + (size_t)r * c.dst_pitch, c.src + (size_t)r * c.src_stride, c.row_bytes);
+}
+
+class CopyPool {
+public:
+    static constexpr int kMaxPieces = 96;
+    static CopyPool &get()
+    {
+        static CopyPool *p = new CopyPool();  // never destroyed: its threads must not be torn down from a static destructor
+        return *p;
+    }
+    // Copies pieces[0..n) with the helpers; `uploaded(i)` is called on the calling thread, in order, once pieces 0..i are
+    // all in place.  Returns false (nothing done) when another picture is using the pool: the caller then copies alone.
+    template <typename F> bool run(const CopyPiece *pieces, int n, F &&uploaded)
+    {
+        std::unique_lock<std::mutex> own(owner_, std::try_to_lock);
+        if (!own.owns_lock() || n > kMaxPieces) return false;
+        start_helpers();
+        for (int i = 0; i < n; i++) done_[i].store(0, std::memory_order_relaxed);
+        pieces_ = pieces;
+        n_ = n;
+        next_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            generation_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        int issued = 0;
+        auto issue_ready = [&] {
+            while (issued < n && done_[issued].load(std::memory_order_acquire)) uploaded(issued++);
+        };
+        for (;;) {
+            const int i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n) break;
+            copy_piece(pieces[i]);
+            done_[i].store(1, std::memory_order_release);
+            issue_ready();
+        }
+        while (issued < n) {
+            issue_ready();
+            if (issued < n) cpu_relax();
+        }
+        // the helpers may still be looking at next_ / pieces_: wait until every one that joined this picture has left it
+        while (inside_.load(std::memory_order_acquire) != 0) cpu_relax();
+        n_ = 0;  // a helper that wakes up only now must not mistake the next picture's table for this one's
+        next_.store(1 << 30, std::memory_order_release);
+        return true;
+    }
+
+private:
+    static void cpu_relax()
+    {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void start_helpers()
+    {
+        if (started_) return;
+        started_ = true;
+        unsigned hw = std::thread::hardware_concurrency();
+        const int helpers = hw >= 8 ? 3 : (hw >= 4 ? 2 : (hw >= 2 ? 1 : 0));
+        for (int i = 0; i < helpers; i++) std::thread([this] { helper_main(); }).detach();
+    }
+    void helper_main()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            // a short spin first: the next picture of a loop arrives within microseconds, a futex wake-up costs tens of them
+            unsigned long long g = generation_.load(std::memory_order_acquire);
+            for (int spin = 0; g == seen && spin < 4000; spin++) {
+                cpu_relax();
+                g = generation_.load(std::memory_order_acquire);
+            }
+            if (g == seen) {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
+                g = generation_.load(std::memory_order_acquire);
+            }
+            seen = g;
+            inside_.fetch_add(1, std::memory_order_acq_rel);
+            // (a helper that wakes up late finds next_ >= n_ -- possibly of a later picture -- and leaves at once; pieces_ and
+            // n_ are only read after a successful claim, and the owner waits for inside_ == 0 before it changes them)
+            for (;;) {
+                const int i = next_.fetch_add(1, std::memory_order_acq_rel);
+                if (i >= n_) break;
+                copy_piece(pieces_[i]);
+                done_[i].store(1, std::memory_order_release);
+            }
+            inside_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    std::mutex owner_;  // one picture at a time
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<unsigned long long> generation_{0};
+    std::atomic<int> next_{1 << 30};
+    std::atomic<int> inside_{0};
+    std::atomic<unsigned char> done_[kMaxPieces];
+    const CopyPiece *pieces_ = nullptr;
+    int n_ = 0;
+    bool started_ = false;
+};
+
 int check_slot(h2j_encoder *e, int slot)
 {
     if (!e) return H2J_ERR_INVALID_ARG;
@@ -417,7 +543,7 @@ int check_slot(h2j_encoder *e, int slot)
 void free_slot(Slot &sl)
 {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_frames); cudaFree(sl.d_pitched); cudaFree(sl.d_images); cudaFree(sl.d_dir); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
+    cudaFree(sl.d_frames); cudaFree(sl.d_pitched); cudaFree(sl.d_images); cudaFree(sl.d_zero); cudaFree(sl.d_stage); cudaFree(sl.d_unit_info);
     cudaFree(sl.d_tabs); cudaFree(sl.d_scan); cudaFree(sl.d_out); cudaFree(sl.d_packed); cudaFree(sl.d_offsets); cudaFree(sl.d_status);
     if (sl.h_offsets) cudaFreeHost(sl.h_offsets);
     if (sl.h_status) cudaFreeHost(sl.h_status);
@@ -536,10 +662,9 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     e->scan_cap_words = (long long)(e->out_cap / 4);
     const int mcu_w = (s->max_width + 15) >> 4, mcu_h = (s->max_height + 15) >> 4;
     const long long n_mcu = (long long)mcu_w * mcu_h;
-    e->images_cap = (n_mcu + kTileMcus - 1) / kTileMcus;
-    e->img_words_cap = e->images_cap * kTileRoles * kSubMaxWords;
+    e->images_cap = ((n_mcu + kTileMcus - 1) / kTileMcus + kEntFdctTiles - 1) / kEntFdctTiles * kEntFdctTiles;
     e->blocks_cap = e->images_cap * kTileBlocks;
-    e->tiles_cap = (int)e->images_cap;
+    e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
     e->units_cap = e->tiles_cap * kEntWarps;
     e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
     // a fixed place of one window per unit, then the reserved area for units that need more (every unit starts on a word:
@@ -570,8 +695,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_begin));
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
-        CUB(cudaMalloc(&sl.d_images, (size_t)e->img_words_cap * 4 * B + 16));  // (+16: K4a may read one word past a list)
-        CUB(cudaMalloc(&sl.d_dir, sizeof(unsigned) * (size_t)e->images_cap * kDirPerTile * B));
+        CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
         const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->groups_cap * B, 256);
         const size_t alloc_bytes = align_up(sizeof(unsigned int) * (size_t)B, 256);
@@ -811,8 +935,8 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
-    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels), uploaded in pieces of
-    // ~512 KiB so that the DMA of one piece runs under the memcpy of the next
+    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels): copied in pieces by this
+    // thread and the copy helpers, every piece uploaded as soon as it is in place
     ON_DEVICE(e);
     const size_t fb = tight_frame_bytes(width, height);
     const size_t dstride = align_up(fb, 256);
@@ -826,21 +950,42 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     sl.n = 1;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     {
-        auto plane = [&](const uint8_t *src, int stride, size_t off, int pw, int pitch, int ph) -> int {
-            const int rows_per_piece = std::max(1, (512 * 1024) / pitch);
+        CopyPiece pieces[CopyPool::kMaxPieces];
+        int n_pieces = 0;
+        auto plane = [&](const uint8_t *src, int stride, size_t off, int pw, int pitch, int ph) {
+            // pieces of ~256 KiB, but never more than a third of the table per plane
+            int rows_per_piece = std::max(1, (256 * 1024) / pitch);
+            rows_per_piece = std::max(rows_per_piece, (ph + CopyPool::kMaxPieces / 3 - 1) / (CopyPool::kMaxPieces / 3));
             for (int r0 = 0; r0 < ph; r0 += rows_per_piece) {
                 const int r1 = std::min(ph, r0 + rows_per_piece);
-                uint8_t *dst = sl.h_stage + off + (size_t)r0 * pitch;
-                if (stride == pw && pitch == pw) memcpy(dst, src + (size_t)r0 * stride, (size_t)(r1 - r0) * pw);
-                else
-                    for (int r = r0; r < r1; r++) memcpy(dst + (size_t)(r - r0) * pitch, src + (size_t)r * stride, pw);
-                CU(e, cudaMemcpyAsync(sl.d_frames + off + (size_t)r0 * pitch, dst, (size_t)(r1 - r0 - 1) * pitch + pw, cudaMemcpyHostToDevice, sl.stream));
+                CopyPiece &c = pieces[n_pieces++];
+                c.dst = sl.h_stage + off + (size_t)r0 * pitch;
+                c.src = src + (size_t)r0 * stride;
+                c.rows = r1 - r0;
+                c.row_bytes = pw;
+                c.dst_pitch = pitch;
+                c.src_stride = stride;
+                c.dev_off = off + (size_t)r0 * pitch;
+                c.dev_bytes = (size_t)(r1 - r0 - 1) * pitch + pw;
             }
-            return H2J_OK;
         };
-        if ((rc = plane(planes[0], strides[0], 0, width, L.y_pitch, height))) return rc;
-        if ((rc = plane(planes[1], strides[1], (size_t)L.u_off, fcw, L.c_pitch, fch))) return rc;
-        if ((rc = plane(planes[2], strides[2], (size_t)L.v_off, fcw, L.c_pitch, fch))) return rc;
+        plane(planes[0], strides[0], 0, width, L.y_pitch, height);
+        plane(planes[1], strides[1], (size_t)L.u_off, fcw, L.c_pitch, fch);
+        plane(planes[2], strides[2], (size_t)L.v_off, fcw, L.c_pitch, fch);
+        cudaError_t up_err = cudaSuccess;
+        auto upload = [&](int i) {
+            const cudaError_t ce = cudaMemcpyAsync(sl.d_frames + pieces[i].dev_off, sl.h_stage + pieces[i].dev_off, pieces[i].dev_bytes, cudaMemcpyHostToDevice, sl.stream);
+            if (ce != cudaSuccess && up_err == cudaSuccess) up_err = ce;
+        };
+        static const bool single_thread = getenv("H2J_STAGE_ONE_THREAD") != nullptr;  // measurement knob
+        if (single_thread || fb < 512 * 1024 || !CopyPool::get().run(pieces, n_pieces, upload)) {
+            // small pictures (waking helpers costs more than it saves), or the helpers are busy with another encoder's picture
+            for (int i = 0; i < n_pieces; i++) {
+                copy_piece(pieces[i]);
+                upload(i);
+            }
+        }
+        CU(e, up_err);
     }
     rc = launch_pipeline(e, sl, sl.d_frames, 1, TAIL_SINGLE);
     if (rc) return rc;
@@ -891,9 +1036,9 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
     if (rc) return rc;
     CU(e, cudaMemcpyAsync(sl.d_frames, sl.h_stage, fb, cudaMemcpyHostToDevice, sl.stream));
     const int pw = L.mcu_w * 16, ph = L.mcu_h * 16;
-    // padded planes are produced in the (otherwise idle) coefficient buffer: 256 bytes per 64 samples, always enough
+    // padded planes are produced in the (otherwise idle) coefficient buffer: 136 bytes per 64 samples, always enough
     const size_t need = (size_t)pw * ph * 3 / 2;
-    if (need > (size_t)e->img_words_cap * 4 * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's scratch buffer");
+    if (need > (size_t)e->images_cap * kTileImageBytes * e->s.max_batch) return fail(e, H2J_ERR_UNSUPPORTED, "padded planes do not fit the slot's scratch buffer");
     uint8_t *oy = reinterpret_cast<uint8_t *>(sl.d_images), *ou = oy + (size_t)pw * ph, *ov = ou + (size_t)pw * ph / 4;
     convert_pad_kernel<<<dim3((pw / 16 + 127) / 128, ph, 3), 128, 0, sl.stream>>>(sl.d_frames, L, range_mode, oy, ou, ov);
     e->launches++;
@@ -943,36 +1088,19 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     if (out_elems < need) return fail(e, H2J_ERR_OUTPUT_TOO_SMALL, "need %zu int16 elements", need);
     ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
-    // compact sub-images -> dense blocks.  The header holds the DC *difference*, so the levels are rebuilt by running the
-    // encoder's predictors (one per component, reset to 128) over the blocks in coding order; an entry's position is the
-    // previous non-zero position + run + 1.
+    // tile images -> dense blocks; halfword 0 of a record is the DC difference, so the levels are rebuilt by
+    // running the encoder's predictors (one per component, reset to 128) over the blocks in coding order
     const int n_tiles = (sl.L.n_mcu + kTileMcus - 1) / kTileMcus;
-    std::vector<uint32_t> img((size_t)n_tiles * kTileRoles * kSubMaxWords);
-    std::vector<unsigned> dirv((size_t)n_tiles * kDirPerTile);
-    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->img_words_cap, img.size() * 4, cudaMemcpyDeviceToHost));
-    CU(e, cudaMemcpy(dirv.data(), sl.d_dir + (size_t)frame * e->images_cap * kDirPerTile, dirv.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    std::vector<int16_t> img((size_t)n_tiles * kTileImageWords * 2);
+    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->images_cap * kTileImageWords, img.size() * sizeof(int16_t),
+                     cudaMemcpyDeviceToHost));
     int last_dc[3] = {128, 128, 128};
     for (int b = 0; b < sl.L.n_blocks; b++) {
-        const TileRec tr = tile_rec(b % kTileBlocks);
-        const unsigned sub_words = dirv[(size_t)(b / kTileBlocks) * kDirPerTile + tr.sub];
-        if (sub_words > (unsigned)kSubMaxWords || sub_words < (unsigned)kSubHdrWords) return fail(e, H2J_ERR_CUDA, "bad directory entry for block %d", b);
-        const uint32_t *sub = img.data() + ((size_t)(b / kTileBlocks) * kTileRoles + tr.sub) * kSubMaxWords;
-        const uint32_t hdr = sub[tr.idx];
+        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords + (size_t)tile_rec_word(b % kTileBlocks)) * 2;
         const int n = b % 6, comp = n < 4 ? 0 : n - 3;
-        int16_t *o = out + (size_t)b * 64;
-        memset(o, 0, 64 * sizeof(int16_t));
-        last_dc[comp] += sub_hdr_diff(hdr);
-        o[0] = (int16_t)last_dc[comp];
-        int pos = 0;
-        for (int i = 0; i < sub_hdr_count(hdr); i++) {
-            const unsigned at = (unsigned)kSubHdrWords + (unsigned)sub_hdr_first(hdr) + (unsigned)i;
-            if (at >= sub_words) return fail(e, H2J_ERR_CUDA, "entry list of block %d leaves its sub-image", b);
-            const uint32_t en = sub[at];
-            pos += entry_run(en) + 1;
-            if (pos > 63) return fail(e, H2J_ERR_CUDA, "entry positions of block %d leave the block", b);
-            o[pos] = (int16_t)entry_level(en);
-        }
-        if ((pos < 63) != (sub_hdr_eob(hdr) != 0)) return fail(e, H2J_ERR_CUDA, "EOB flag of block %d contradicts its entries", b);
+        last_dc[comp] += rec[0];
+        out[(size_t)b * 64] = (int16_t)last_dc[comp];
+        for (int k = 1; k < 64; k++) out[(size_t)b * 64 + k] = rec[2 * (k & 31) + (k >> 5)];
     }
     return H2J_OK;
 }

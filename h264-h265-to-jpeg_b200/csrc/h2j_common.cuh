@@ -34,40 +34,33 @@ struct FrameLayout {
     int nv12;          // chroma is ONE plane of interleaved Cb/Cr pairs at u_off, rows c_pitch apart (v_off unused)
 };
 
-// ---- coefficient store (compact sub-images + directory) ------------------------------------------
-// K2 works on tiles of 16 consecutive MCUs (96 blocks), three single-warp roles per tile:
-//   role 0: the 32 luma blocks of MCUs 0..7  (record index = mcu * 4 + n)
-//   role 1: the 32 luma blocks of MCUs 8..15
-//   role 2: Cb of the 16 MCUs (records 0..15), Cr (records 16..31)
-// About nine levels in ten are zero after quantisation, so a role's 32 blocks leave K2 as a COMPACT sub-image that holds
-// only what K4a codes (r1: dense records of 136 bytes per block -- 6.66 MB written and read again per 1080p frame):
-//   words 0..31   block headers, in record order
-//                   [31:20] DC difference to the previous block of the component (signed: what gets coded)
-//                   [19]    the block ends before position 63: an EOB symbol is coded
-//                   [18:12] number of entries (0..63)
-//                   [11:0]  index of its first entry, counted from word 32
-//   words 32..    entries, the blocks' lists back to back in record order, one per non-zero AC level in zigzag order:
-//                   [31:16] level (signed)
-//                   [9:4]   run of zeros in front of it (0..62): [9:8] ZRL symbols to emit first, [7:4] the symbol's run nibble
-//                   [3:0]   magnitude category - 1 (0..10) -- so [7:0] + 1 is the level's Huffman symbol
-// K4a never looks at positions or masks: it maps entry -> code and appends.  Sub-image (tile, role) of a frame starts at
-// word (tile * 3 + role) * kSubMaxWords of the frame's region (room for its densest form; only the words in use are ever
-// written or read -- in 16-byte granules, what the bulk copies move); the directory holds its length in words.
+// ---- coefficient store ("tile images") -----------------------------------------------------------
+// K2 works on tiles of 16 consecutive MCUs (96 blocks).  A tile leaves K2 as one contiguous image made of three
+// sub-images, one per K2 warp, so that every warp can send its part on its own (no CTA barrier in K2's tile loop):
+//   sub-image 0: the 32 luma blocks of MCUs 0..7  (record index = mcu * 4 + n)
+//   sub-image 1: the 32 luma blocks of MCUs 8..15
+//   sub-image 2: Cb of the 16 MCUs (records 0..15), Cr (records 16..31)
+// A sub-image is 32 block records of 33 words each, then 32 words of high mask halves.
+//   record word j (0..31)  low half: level j, high half: level j + 32 of the zigzag scan (this pairing lets K2
+//                          derive the non-zero mask from packed 16-bit minima); level 0 is stored as the DC
+//                          *difference* to the previous block of the same component, i.e. what gets coded
+//   record word 32         non-zero mask of levels 1..31 (bit k = level k != 0, bit 0 clear).  It also makes the
+//                          record stride odd in words: K2's lanes write their records without bank conflicts
+//   word 1056 + r          non-zero mask of levels 32..63 of record r
+// The image is assembled in shared memory and moved with bulk (TMA) copies: three stores of 4,352 bytes by K2, ONE
+// load of two images by K4a.
 constexpr int kTileMcus = 16;
 constexpr int kTileBlocks = kTileMcus * 6;                  // 96
+constexpr int kBlkWords = 33;
+constexpr int kBlkHalf = kBlkWords * 2;                     // 66
+constexpr int kMaskLoWord = 32;                             // inside the record
 constexpr int kSubRecs = 32;
-constexpr int kSubHdrWords = kSubRecs;                      // 32
-constexpr int kSubMaxWords = kSubHdrWords + kSubRecs * 63;  // 2048: every AC level of every block non-zero
-constexpr int kTileRoles = 3;
-constexpr int kDirPerTile = 4;                              // directory words per tile (three used): 16 bytes, one vector load
-__host__ __device__ inline uint32_t sub_hdr_pack(int dc_diff, int eob, int count, int first) { return ((uint32_t)dc_diff << 20) | ((uint32_t)eob << 19) | ((uint32_t)count << 12) | (uint32_t)first; }
-__host__ __device__ inline int sub_hdr_diff(uint32_t h) { return (int)h >> 20; }
-__host__ __device__ inline int sub_hdr_eob(uint32_t h) { return (int)((h >> 19) & 1u); }
-__host__ __device__ inline int sub_hdr_count(uint32_t h) { return (int)((h >> 12) & 0x7fu); }
-__host__ __device__ inline int sub_hdr_first(uint32_t h) { return (int)(h & 0xfffu); }
-__host__ __device__ inline int entry_level(uint32_t e) { return (int)e >> 16; }
-__host__ __device__ inline int entry_run(uint32_t e) { return (int)((e >> 4) & 0x3fu); }
-// block b of a tile (0..95 in coding order: Y0 Y1 Y2 Y3 Cb Cr per MCU) -> (role, record)
+constexpr int kSubMaskHiOff = kSubRecs * kBlkWords;         // 1056
+constexpr int kSubImageWords = kSubMaskHiOff + kSubRecs;    // 1088
+constexpr int kSubImageBytes = kSubImageWords * 4;          // 4352 = 272 * 16
+constexpr int kTileImageWords = 3 * kSubImageWords;         // 3264
+constexpr int kTileImageBytes = kTileImageWords * 4;        // 13056 = 816 * 16
+// block b of a tile (0..95 in coding order: Y0 Y1 Y2 Y3 Cb Cr per MCU) -> (sub-image, record)
 struct TileRec { int sub, idx; };
 __host__ __device__ inline TileRec tile_rec(int b)
 {
@@ -77,12 +70,16 @@ __host__ __device__ inline TileRec tile_rec(int b)
     else { r.sub = 2; r.idx = (n - 4) * 16 + m; }
     return r;
 }
-// K2's scratch record of a block: word j holds levels j (low half) and j + 32 (high half) of the zigzag scan -- the pairing
-// lets K2 derive the non-zero masks from packed 16-bit minima -- at an odd stride (conflict-free writes, lane = record)
-constexpr int kBlkWords = 33;
+__host__ __device__ inline int tile_rec_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + r.idx * kBlkWords; }
+__host__ __device__ inline int tile_maskhi_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + kSubMaskHiOff + r.idx; }
 constexpr int kFdctThreads = 32;                           // K2: single-warp CTAs, three roles per tile
 
-constexpr int kEntThreads = kTileBlocks;                    // K4a: one CTA per K2 tile, one thread per block (two tiles per CTA measured 3 % slower)
+#ifndef H2J_ENT_FDCT_TILES
+#define H2J_ENT_FDCT_TILES 1
+#endif
+constexpr int kEntFdctTiles = H2J_ENT_FDCT_TILES;            // K2 tiles per K4a CTA: 1 (0.749 ms at 512 x 1080p) against 2 (0.775 ms)
+constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192
+constexpr int kEntThreads = kEntBlocks;
 constexpr int kMaxBitsPerBlock = 27 * 64;                   // DC (16+11) + 63 * (16+11); ZRLs only replace coefficients
 
 constexpr int kHuffGroup = 128;                             // threads per table
@@ -119,7 +116,6 @@ struct FrameState {
     unsigned long long scan_bits;   // written by the frame's last K4b group
     unsigned int k1_done;           // K1 CTAs that have added their share of var_sum
     unsigned int k3_done;           // K3 CTAs (one per table) that have finished: the fourth writes the header
-    unsigned int pad_[2];
     unsigned int hist[4][256];      // DC luma, DC chroma, AC luma, AC chroma symbol counts (K2)
 };
 

@@ -1,11 +1,9 @@
 // K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame), in two kernels.
 //
 // K4a entropy_walk_kernel -- all the coding work, no dependency between CTAs or warps:
-//   A CTA takes one K2 tile of one frame (96 consecutive blocks): thread 0 reads the tile's three directory entries and
-//   pulls the three compact sub-images (block headers + one entry per non-zero level, h2j_common.cuh) and the frame's
-//   code tables into shared memory with bulk copies (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier; a tile
-//   whose sub-images outgrow the shared-memory image (dense content) is read from global memory where it lies.
-//   Each of the CTA's warps then works alone on its UNIT of 32 blocks:
+//   A CTA takes kEntFdctTiles K2 tiles of one frame (one: 96 consecutive blocks) and pulls the tile image (levels
+//   and non-zero masks) and the frame's code tables into shared memory with bulk copies (cp.async.bulk -> SASS
+//   UBLKCP) signalled on an mbarrier.  Each of the CTA's warps then works alone on its UNIT of 32 blocks:
 //     1. ONE walk over the block: every lane encodes its block into a private 256-bit slot in shared memory and
 //        learns its bit length on the way (a block that needs more keeps counting and is emitted directly in 2);
 //        warp scan of the lengths.
@@ -61,7 +59,7 @@ constexpr int kSlotStride = kSlotWords + 1;                  // odd stride: the 
 #ifndef H2J_ENT_PREFETCH_DISTANCE
 #define H2J_ENT_PREFETCH_DISTANCE 1024
 #endif
-constexpr int kEntPrefetchDistance = H2J_ENT_PREFETCH_DISTANCE;  // K4a: CTAs ahead whose directory line is requested into L2
+constexpr int kEntPrefetchDistance = H2J_ENT_PREFETCH_DISTANCE;  // K4a: CTAs ahead whose image is requested into L2 (148 SMs x 10 CTAs are resident)
 constexpr int kPlaceGroupUnits = 256;                        // K4b: units per CTA, one per thread
 constexpr int kPlaceThreads = 256;
 #ifndef H2J_PLACE_BATCH
@@ -141,133 +139,145 @@ struct SlotSink {  // MSB-first into the lane's private slot; keeps counting (an
     __device__ __forceinline__ void flush() { if (fill > 0 && widx < kSlotWords) slot[widx] = (unsigned)(acc << (32 - fill)); }
 };
 
-// One pass over a block: DC difference, then its entries in order (each one is a complete symbol: run, size and level
-// are in the entry -- no positions, no masks), then EOB.  Two entries per trip: their loads and code look-ups are
-// independent and overlap; only the emission is in order.
-template <typename Sink>
-__device__ __forceinline__ void walk_block(const uint32_t *__restrict__ list, uint32_t hdr, const uint32_t *__restrict__ hdc,
-                                           const uint32_t *__restrict__ hac, Sink *sink)
+// One pass over a block.  EMIT=false: returns the bit length.  EMIT=true: writes the bits into `sink`.
+// cb = the block's 66-halfword record in shared memory ([0] = DC difference, level k at [2*(k&31) + (k>>5)]).
+template <bool EMIT, typename Sink>
+__device__ __forceinline__ unsigned walk_block(const int16_t *cb, unsigned mask_lo, unsigned mask_hi, const uint32_t *__restrict__ hdc,
+                                               const uint32_t *__restrict__ hac, Sink *sink)
 {
+    unsigned total = 0;
     {
-        const int diff = sub_hdr_diff(hdr);
+        const int diff = (int)cb[0];
         const int nb = mag_bits(diff);
         const uint32_t e = hdc[nb];  // code tables come pre-shifted from K3: (code << nb) << 5 | (code length + nb)
-        const unsigned mant = (unsigned)(diff + (diff >> 31)) & ((1u << nb) - 1u);
-        sink->put((e >> 5) | mant, (int)(e & 31));
+        if (EMIT) {
+            const unsigned mant = (unsigned)(diff + (diff >> 31)) & ((1u << nb) - 1u);
+            sink->put((e >> 5) | mant, (int)(e & 31));
+        } else total += e & 31;
     }
+    int prev = 0;
     const uint32_t zrl = hac[0xf0];
-    auto code_one = [&](uint32_t en, uint32_t h) {
-        if (en & 0x300u)
-            for (int z = (int)((en >> 8) & 3u); z > 0; z--) sink->put(zrl >> 5, (int)(zrl & 31));
-        const int nb = (int)(en & 15u) + 1, lvl = entry_level(en);
-        const unsigned mant = (unsigned)(lvl + (lvl >> 31)) & ((1u << nb) - 1u);
-        sink->put((h >> 5) | mant, (int)(h & 31));
+    // one coded level: zero-run escapes, then (run, size) code + mantissa
+    auto code_one = [&](int run, int val, int nb, uint32_t e) {
+        if (run >= 16) {
+            if (EMIT) {
+                for (int z = run >> 4; z > 0; z--) sink->put(zrl >> 5, zrl & 31);
+            } else total += (unsigned)(run >> 4) * (zrl & 31);
+        }
+        if (EMIT) {
+            const unsigned mant = (unsigned)(val + (val >> 31)) & ((1u << nb) - 1u);
+            sink->put((e >> 5) | mant, (int)(e & 31));
+        } else total += e & 31;
     };
-    const int cnt = sub_hdr_count(hdr);
-    for (int i = 0; i < cnt; i += 2) {
-        const uint32_t e0 = list[i];
-        const uint32_t e1 = list[i + 1];  // (one word past the list at the most: inside the image / the region's slack)
-        const uint32_t h0 = hac[1 + (e0 & 0xffu)], h1 = hac[1 + (e1 & 0xffu)];  // (entry: size - 1; the + 1 rides in the address)
-        code_one(e0, h0);
-        if (i + 1 < cnt) code_one(e1, h1);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        unsigned mm = half ? mask_hi : mask_lo;
+        // kWalkPerTrip positions per trip: their position -> level -> size -> code look-ups are independent and overlap;
+        // only the emission is in order (positions a lane has run out of are predicated off)
+        while (mm) {
+            unsigned b[kWalkPerTrip];
+            int k[kWalkPerTrip], val[kWalkPerTrip], nb[kWalkPerTrip], run[kWalkPerTrip];
+            uint32_t e[kWalkPerTrip];
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++) {
+                b[i] = mm & (0u - mm);
+                mm ^= b[i];
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++) {
+                const int p = (i == 0 || b[i]) ? 31 - __clz(b[i]) : k[i - 1] - half * 32;  // absent: the previous position again
+                k[i] = half * 32 + p;
+                val[i] = (int)cb[2 * p + half];
+                nb[i] = mag_bits(val[i]);
+                run[i] = k[i] - (i ? k[i - 1] : prev) - 1;
+                e[i] = hac[((run[i] & 15) << 4) | nb[i]];
+            }
+#pragma unroll
+            for (int i = 0; i < kWalkPerTrip; i++)
+                if (i == 0 || b[i]) code_one(run[i], val[i], nb[i], e[i]);
+            prev = k[kWalkPerTrip - 1];
+        }
     }
-    if (sub_hdr_eob(hdr)) {
+    if (prev < 63) {
         const uint32_t e = hac[0];
-        sink->put(e >> 5, (int)(e & 31));
+        if (EMIT) sink->put(e >> 5, e & 31);
+        else total += e & 31;
     }
+    return total;
 }
 
 constexpr int kEntTabBytes = (2 * 16 + 2 * 256) * 4;  // DC luma/chroma (16 entries each), AC luma/chroma of FrameTab::hcode
-#ifndef H2J_ENT_IMG_WORDS
-#define H2J_ENT_IMG_WORDS 1536
-#endif
-constexpr int kEntImgWords = H2J_ENT_IMG_WORDS;  // shared-memory image of a tile's three sub-images: 96 headers + up to 1428 entries
-                                                  // (~15 non-zero levels per block); denser tiles are read from global memory
-constexpr int kEntSmemBytes = (kEntImgWords + 4) * 4 + kEntTabBytes + kEntWarps * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
+constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + kEntTabBytes + kEntWarps * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
 static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0, "hcode must be bulk-copyable");
 
 // grid (tiles_per_frame, frames)
 __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L, FrameTab *__restrict__ tabs,
-                                                                   const uint32_t *__restrict__ images, long long img_words_cap,
-                                                                   const unsigned *__restrict__ dir, long long images_cap,
+                                                                   const uint32_t *__restrict__ images, long long images_cap,
                                                                    unsigned long long *__restrict__ unit_info, int units_cap,
                                                                    unsigned int *__restrict__ stage_alloc,  // [frame] words handed out
                                                                    uint32_t *__restrict__ stage, long long stage_cap_words)
 {
     extern __shared__ __align__(128) unsigned char ent_smem[];
-    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                            // the tile's sub-images, back to back
-    uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + (kEntImgWords + 4) * 4);   // [2][16] DC code tables
-    uint32_t *s_hac = s_hdc + 32;                                                        // [2][256] AC code tables
-    unsigned int *s_win_all = s_hac + 512;                                               // [warp][kWarpWinStride]
-    unsigned int *s_slot_all = s_win_all + kEntWarps * kWarpWinStride;                   // [warp][lane][kSlotStride]
+    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                    // the CTA's tile images
+    uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [2][16] DC code tables
+    uint32_t *s_hac = s_hdc + 32;                                                                // [2][256] AC code tables
+    unsigned int *s_win_all = s_hac + 512;                                                       // [warp][kWarpWinStride]
+    unsigned int *s_slot_all = s_win_all + kEntWarps * kWarpWinStride;                           // [warp][lane][kSlotStride]
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ unsigned s_sub_at[kTileRoles];    // first word of the role's sub-image in s_img
-    __shared__ int s_in_smem;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.y, tile = blockIdx.x;
-    const uint32_t *gimg = images + (long long)f * img_words_cap;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
-        // words of the tile's three sub-images: one 16-byte directory line
-        const uint4 d = __ldg(reinterpret_cast<const uint4 *>(dir + ((long long)f * images_cap + tile) * kDirPerTile));
-        const unsigned w16[kTileRoles] = {(d.x + 3u) & ~3u, (d.y + 3u) & ~3u, (d.z + 3u) & ~3u};  // what K2 copied out
-        const unsigned total = w16[0] + w16[1] + w16[2];
-        const bool in_smem = total <= (unsigned)kEntImgWords;
-        mbar_expect_tx(&s_bar, (in_smem ? total * 4u : 0u) + kEntTabBytes);
-        unsigned at = 0;
-#pragma unroll
-        for (int r = 0; r < kTileRoles; r++) {
-            s_sub_at[r] = at;
-            if (in_smem) bulk_g2s(s_img + at, gimg + ((long long)tile * kTileRoles + r) * kSubMaxWords, w16[r] * 4u, &s_bar);
-            at += w16[r];
-        }
-        s_in_smem = in_smem ? 1 : 0;
+        // images_cap is even, so both images of the tile exist in the buffer even when the second holds no block
+        const uint32_t *src = images + ((long long)f * images_cap + (long long)tile * kEntFdctTiles) * kTileImageWords;
+        mbar_expect_tx(&s_bar, kEntFdctTiles * kTileImageBytes + kEntTabBytes);
+        bulk_g2s(s_img, src, kEntFdctTiles * kTileImageBytes, &s_bar);
         bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
         bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
-        // CTAs are dispatched in linear order: ask for the directory line of a CTA that starts a fraction of a CTA lifetime
-        // from now to be brought into L2 (that CTA's first, dependent load then finds it there)
+        // CTAs are dispatched in linear order, so this one asks for the image of a CTA that starts a fraction of a CTA
+        // lifetime (~4 us) from now to be brought into L2; that CTA's bulk copy then finds it there.  Worth 1.3 % of the
+        // kernel (any distance from 384 to 2048 CTAs measures the same, 4096 is 12 % slower): most of the wait behind
+        // the mbarrier is not DRAM latency.
         const long long lin = (long long)f * gridDim.x + tile + kEntPrefetchDistance;
         if (lin < (long long)gridDim.x * gridDim.y) {
             const long long f2 = lin / gridDim.x, t2 = lin - f2 * gridDim.x;
-            bulk_prefetch_l2(dir + (f2 * images_cap + t2) * kDirPerTile, 16);
+            bulk_prefetch_l2(images + (f2 * images_cap + t2 * kEntFdctTiles) * kTileImageWords, kEntFdctTiles * kTileImageBytes);
         }
     }
-    static_assert((kEntWarps * kWarpWinStride) % 4 == 0 && ((kEntImgWords + 4) * 4 + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
+    static_assert((kEntWarps * kWarpWinStride) % 4 == 0 && (kEntFdctTiles * kTileImageBytes + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
     for (int i = tid; i < kEntWarps * kWarpWinStride / 4; i += kEntThreads) reinterpret_cast<uint4 *>(s_win_all)[i] = make_uint4(0, 0, 0, 0);  // while the copies are on their way
-    __syncthreads();  // barrier initialised, windows cleared, directory known
+    __syncthreads();  // barrier initialised, windows cleared (clearing only the words a unit needs, once its length is
+                      // known, executes fewer instructions but measured 1 % slower: here it hides under the copy)
 
     // ---- from here on the warp is on its own ----
     const int u = tile * kEntWarps + warp;                  // unit index inside the frame
-    const int b = u * kUnitBlocks + lane;                   // == tile * kTileBlocks + tid
+    const int b = u * kUnitBlocks + lane;                   // == tile * kEntBlocks + tid
     if (u * kUnitBlocks >= L.n_blocks) return;              // trailing unit of the frame's last tile: no block at all
     const bool valid = b < L.n_blocks;
-    const TileRec tr = tile_rec(tid);                       // block inside the tile (coding order) -> (role, record)
-    const int cls = (tid % 6) < 4 ? 0 : 1;                  // 96 is a multiple of 6: the block's position in its MCU is tid % 6
+    const int img_i = tid >= kTileBlocks ? 1 : 0, blk_i = tid - img_i * kTileBlocks;  // K2 image, block inside it (coding order)
+    const uint32_t *rec = s_img + img_i * kTileImageWords + tile_rec_word(blk_i);
+    const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
+    const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
     const uint32_t *hdc = s_hdc + 16 * cls, *hac = s_hac + 256 * cls;
     unsigned int *win = s_win_all + warp * kWarpWinStride;
     unsigned int *slot = s_slot_all + (warp * kUnitBlocks + lane) * kSlotStride;
     uint32_t *st = stage + (long long)f * stage_cap_words;
-    const bool in_smem = s_in_smem != 0;                    // (CTA-uniform)
-    // the sub-image this lane's block lives in: in shared memory, or (dense tile) where K2 put it
-    const uint32_t *sub_s = s_img + s_sub_at[tr.sub];
-    const uint32_t *sub_g = gimg + ((long long)tile * kTileRoles + tr.sub) * kSubMaxWords;
 
-    mbar_wait(&s_bar, 0);  // sub-images and code tables landed
-    uint32_t hdr = 0;
-    if (valid) hdr = in_smem ? sub_s[tr.idx] : __ldg(sub_g + tr.idx);
-    const uint32_t *list_s = sub_s + kSubHdrWords + sub_hdr_first(hdr);
-    const uint32_t *list_g = sub_g + kSubHdrWords + sub_hdr_first(hdr);
-    const uint32_t *list = in_smem ? list_s : list_g;       // (generic: the rare re-walks below)
+    mbar_wait(&s_bar, 0);  // coefficient images and code tables landed
+    unsigned mask_lo = 0, mask_hi = 0;
+    if (valid) {
+        mask_lo = rec[kMaskLoWord];
+        mask_hi = s_img[img_i * kTileImageWords + tile_maskhi_word(blk_i)];
+    }
 
     // ---- 1. the walk: bits into the private slot, length on the way ----
     unsigned len = 0;
     if (valid) {
         SlotSink ss;
         ss.init(slot);
-        if (in_smem) walk_block<SlotSink>(list_s, hdr, hdc, hac, &ss);
-        else walk_block<SlotSink>(list_g, hdr, hdc, hac, &ss);
+        walk_block<true, SlotSink>(cb, mask_lo, mask_hi, hdc, hac, &ss);
         len = ss.bits();
         ss.flush();
     }
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
             } else {
                 BitSink sink;
                 sink.init(win, off);
-                walk_block<BitSink>(list, hdr, hdc, hac, &sink);
+                walk_block<true, BitSink>(cb, mask_lo, mask_hi, hdc, hac, &sink);
                 sink.flush();
             }
         }
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
             if (valid && off < hi && off + len > lo) {
                 BitSinkClip sink;
                 sink.init(win, off, lo, hi);
-                walk_block<BitSinkClip>(list, hdr, hdc, hac, &sink);
+                walk_block<true, BitSinkClip>(cb, mask_lo, mask_hi, hdc, hac, &sink);
             }
             __syncwarp();
             const unsigned nw = (hi - lo + 31) >> 5, w0 = lo >> 5;

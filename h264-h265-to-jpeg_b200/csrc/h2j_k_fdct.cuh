@@ -16,14 +16,8 @@
 // output of ff_fdct_sse2 is exactly the sum of the 64 samples (8 * column sums, then (8*S*16384 + 65536) >> 17
 // == S), so eight lanes add one pixel row each -- no second FDCT.
 //
-// What leaves the kernel is the role's COMPACT sub-image of the tile (h2j_common.cuh): a header word per block and one
-// entry per non-zero AC level.  The quantised levels are first written to a scratch record per lane in shared memory
-// (registers cannot be indexed by a position found at run time); the statistics walk, which visits every non-zero level
-// anyway to count its (run, size) symbol, appends the level's entry -- level, run, size -- to the lane's list in the
-// staging buffer, at the offset a warp scan of the non-zero counts gave it.  The sub-image goes to the place its
-// (tile, role) owns in the frame's region with ONE bulk (TMA) store of exactly its length, and the (tile, role) directory
-// entry records that length.  A sub-image whose lists outgrow the staging buffer (more than 30 non-zero levels per block on
-// average) leaves in two pieces, sixteen blocks each.
+// The tile image (h2j_common.cuh) is three sub-images, one per role.  A warp assembles its sub-image in one of its two
+// shared-memory buffers and sends it with its own bulk (TMA) store.
 // Pixel rows of the next tile are requested before the statistics of the current one are taken, so their latency
 // is covered by work.
 //
@@ -31,8 +25,10 @@
 #pragma once
 #include "h2j_common.cuh"
 
-// (the walk takes two positions per trip from the low end.  K2 per 2048 frames, r1: two-ended 5.538 ms, 2 per trip 5.511,
-// 3 per trip 5.592, 4 per trip 5.626 -- absent positions are predicated off)
+#ifndef H2J_K2_WALK
+#define H2J_K2_WALK 2  // positions the statistics walk takes per trip from the low end (0: the two-ended walk).  K2 per 2048 frames:
+                      // two-ended 5.538 ms, 2 per trip 5.511, 3 per trip 5.592, 4 per trip 5.626 (absent positions are predicated off)
+#endif
 #ifndef H2J_FDCT_MIN_CTAS
 #define H2J_FDCT_MIN_CTAS 16  // resident single-warp CTAs per SM the register allocation is bounded for (16 -> 128 registers)
 #endif
@@ -191,21 +187,14 @@ __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const Plan
     return s;
 }
 
-constexpr int kFdctStageWords = 1088;  // staging buffer of a warp: 32 headers + up to 1056 entries (4.25 KiB); half a sub-image
-                                       // at its densest (16 blocks x 63 entries + the headers) always fits
-static_assert(kSubHdrWords + 16 * 63 <= kFdctStageWords, "half a sub-image must fit the staging buffer");
-
 template <bool NV12>
 __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
                                                                      FrameState *__restrict__ state,
                                                                      const FrameTab *__restrict__ tabs,
-                                                                     uint32_t *__restrict__ images,  // [frame][img_words_cap] coefficient regions
-                                                                     long long img_words_cap,
-                                                                     unsigned *__restrict__ dir,     // [frame][images_cap][kDirPerTile] words of each sub-image
+                                                                     uint32_t *__restrict__ images,  // [frame][images_cap] tile images
                                                                      long long images_cap, int tiles_per_cta)
 {
-    __shared__ __align__(128) uint32_t s_out[kFdctStageWords];
-    __shared__ uint32_t s_rec[kSubRecs * kBlkWords];
+    __shared__ __align__(128) uint32_t s_img[2][kSubImageWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
     __shared__ unsigned int s_hist[256];
@@ -257,10 +246,14 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
     __syncwarp();
 
     int chroma_carry = 128;  // chroma warp, lanes 0 / 16: DC of the previous tile's last Cb / Cr block
-    uint32_t *gimg = images + (long long)f * img_words_cap;
 
     for (int tile = tile0; tile < tile_end; tile++) {
+        // this warp's sub-image of the tile, in one of its two buffers; the store that used this buffer two tiles ago must
+        // have read it out (lane 0 issued it, lane 0 waits)
+        uint32_t *img = s_img[(tile - tile0) & 1];
         const bool valid = bp.m < L.n_mcu;
+        if (lane == 0) bulk_wait_read_but_one();
+        __syncwarp();
 
         // ---- predecessor DC for the first lane(s) of the warp, from pixel sums ----
         int psum = nvc ? fetch_pred_rowsum<true>(F, Q, pp, phelp_at(tile), lane & 7, lut) : fetch_pred_rowsum<false>(F, Q, pp, phelp_at(tile), lane & 7, lut);
@@ -276,8 +269,9 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
         else pred_first = chroma_carry;
 
         unsigned mask_lo = 0, mask_hi = 0;
+        uint32_t word0_hi = 0;
         int dc = 0;
-        uint32_t *rec = s_rec + lane * kBlkWords;  // scratch record (this lane writes it, this lane reads it back)
+        uint32_t *rec = img + lane * kBlkWords;  // the lane order of every warp is its record order
         if (valid) {
             int v[64];
             if (nvc) fetch_consume<true>(F, R, bp, lut, v);
@@ -297,10 +291,13 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
                 const unsigned t = __vminu2(w, 0x00010001u);
                 if (j < 16) fa += t << j;
                 else fb += t << (j - 16);
-                rec[j] = w;  // (word 0: low half unused, high half = level 32)
+                if (j == 0) word0_hi = w;  // the low half becomes the DC difference below
+                else rec[j] = w;
             }
             mask_lo = ((fa & 0xffffu) | (fb << 16)) & ~1u;  // bit 0 is the DC position: always coded, never in the mask
             mask_hi = (fa >> 16) | (fb & 0xffff0000u);
+            rec[kMaskLoWord] = mask_lo;
+            img[kSubMaskHiOff + lane] = mask_hi;
         }
 
         // ---- request the next tile's pixels: nothing of this tile's 64-value block is live any more ----
@@ -311,122 +308,89 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_ke
             else fetch_issue<false, false>(F, safe, R, bp, bp.m < L.n_mcu, Q, pp, phelp_at(tile + 1), lane & 7);
         }
 
-        // ---- where the lists go: a warp scan of the non-zero counts ----
-        const int cnt = __popc(mask_lo) + __popc(mask_hi);  // (0 for blocks that do not exist)
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        // the (tile, role)'s own place in the frame's region.  (A bump allocator -- one atomicAdd per sub-image, for densely
-        // packed regions -- measured slower: all warps working on a frame queue up on one address, and lane 0 then waits for
-        // the answer when it issues the store: 5 % of the kernel's stall samples.)
-        uint32_t *gsub = gimg + ((long long)tile * kTileRoles + warp) * kSubMaxWords;
-
         // ---- DC difference to the previous block of the same component (mjpegenc.c encode_block) ----
         const int up = __shfl_up_sync(0xffffffffu, dc, 1);
         const int pred = (luma ? lane == 0 : (lane & 15) == 0) ? pred_first : up;
         const int last = __shfl_sync(0xffffffffu, dc, (lane & 16) | 15);  // chroma: this tile's last Cb / Cr
         chroma_carry = last;
-        const int diff = dc - pred;
         if (valid) {
+            const int diff = dc - pred;
+            rec[0] = (uint32_t)(diff & 0xffff) | word0_hi;
             atomicAdd(&s_dchist[mag_bits(diff)], 1u);
-            if (!(mask_hi >> 31)) atomicAdd(&s_hist[0], 1u);  // position 63 is zero: the block ends with an EOB
-        }
-
-        // The block's entry list (ff_mjpeg_encode_coef / record_block, AC part): one entry per non-zero level.  The
-        // (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level below it and
-        // its value.  Positions are taken in ascending order, two at a time: two independent bit-scan -> load -> size
-        // chains per iteration instead of one, half the trips.
-        auto walk_into = [&](uint32_t *dst) {
+            // ---- AC symbol statistics (ff_mjpeg_encode_coef / record_block, AC part) ----
+            // The (run, size) symbol of a non-zero level needs only its position, the position of the non-zero level
+            // below it and its value, so the levels can be visited in any order.  Positions 1..31 (where nearly all of
+            // them are) are taken two at a time: two independent bit-scan -> load -> size -> atomic chains per
+            // iteration instead of one, half the trips.
             const int16_t *lv = reinterpret_cast<const int16_t *>(rec);
-            uint32_t *dst_hi = dst + __popc(mask_lo);
-            auto put = [&](uint32_t *at, int k, int below, int val) {  // val != 0
+            unsigned int *hist = s_hist;
+            unsigned zrl = 0;  // 16-zero runs (symbol 0xF0): summed here, one update per block
+            auto count = [&](int k, int below, int val) {  // val != 0
                 const int run = k - below - 1;
-                unsigned top;  // size - 1
+                unsigned top;  // size - 1: the + 1 rides in the address (size <= 15, no carry into the run nibble)
                 asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(val)));
-                *at = ((unsigned)val << 16) | (unsigned)((run << 4) + (int)top);  // entry: level | run << 4 | (size - 1)
+                zrl += (unsigned)run >> 4;
+                atomicAdd(&hist[1 + (((run & 15) << 4) | (int)top)], 1u);
             };
             unsigned lo = mask_lo;
+            const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
+#if H2J_K2_WALK
+            // H2J_K2_WALK positions per trip, taken from the low end, without a branch inside: the chains (position -> level
+            // -> size -> histogram) are independent, the ones a lane does not have are predicated off
             int below = 0;
             while (lo) {
                 const unsigned b0 = lo & (0u - lo);
                 lo ^= b0;
                 const unsigned b1 = lo & (0u - lo);
                 lo ^= b1;
-                const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1);  // k1 = -1: absent (then this was the last trip)
+                const unsigned b2 = H2J_K2_WALK >= 3 ? lo & (0u - lo) : 0u;
+                lo ^= b2;
+                const unsigned b3 = H2J_K2_WALK >= 4 ? lo & (0u - lo) : 0u;
+                lo ^= b3;
+                const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1), k2 = 31 - __clz(b2), k3 = 31 - __clz(b3);  // -1: absent
                 const int v0 = (int)lv[2 * k0], v1 = (int)lv[2 * max(k1, 0)];
-                put(dst, k0, below, v0);
-                if (b1) put(dst + 1, k1, k0, v1);
-                dst += 2;
-                below = k1;
+                count(k0, below, v0);
+                if (b1) count(k1, k0, v1);
+                if (H2J_K2_WALK >= 3 && b2) count(k2, k1, (int)lv[2 * max(k2, 0)]);
+                if (H2J_K2_WALK >= 4 && b3) count(k3, k2, (int)lv[2 * max(k3, 0)]);
+                below = 31 - __clz(b0 | b1 | b2 | b3);
             }
-            int prev = mask_lo ? 31 - __clz(mask_lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
+#else
+            int below_a = 0;   // ascending end: the non-zero position below the next one taken
+            int kb = top_lo;   // descending end: the highest position still in `lo`
+            while (lo) {
+                const unsigned bit_a = lo & (0u - lo);
+                const int ka = 31 - __clz(bit_a);
+                lo ^= bit_a;
+                const int val_a = (int)lv[2 * ka];
+                if (lo) {  // ka was not the last one: kb is a different position
+                    lo ^= 1u << kb;
+                    const int val_b = (int)lv[2 * kb];
+                    const int below_b = lo ? 31 - __clz(lo) : ka;  // next one down, or the one the other end just took
+                    count(kb, below_b, val_b);
+                    kb = below_b;
+                }
+                count(ka, below_a, val_a);
+                below_a = ka;
+            }
+#endif
+            int prev = top_lo;
             unsigned hi = mask_hi;
             while (hi) {
                 const int bp = __ffs((int)hi) - 1, k = 32 + bp;
                 hi &= hi - 1;
-                put(dst_hi++, k, prev, (int)lv[2 * bp + 1]);
+                count(k, prev, (int)lv[2 * bp + 1]);
                 prev = k;
             }
-        };
-        // Symbol statistics of finished lists, a lane per entry (every lane busy, unlike in the walk): (run & 15, size)
-        // counts and 16-zero runs (symbol 0xF0)
-        auto count_entries = [&](int e0, int e1) {
-#pragma unroll 1
-            for (int i = e0 + lane; i < e1; i += 32) {
-                const unsigned e = s_out[i];
-                atomicAdd(&s_hist[1 + (e & 0xffu)], 1u);  // (the symbol's size nibble is the entry's + 1: rides in the address)
-                if (e & 0x300u) atomicAdd(&s_hist[0xf0], (e >> 8) & 3u);  // runs of 16 and more are rare
-            }
-        };
-
-        // the store of the previous tile must have read the staging buffer out (lane 0 issued it, lane 0 waits; it had a
-        // whole transform's time to do so)
-        if (lane == 0) bulk_wait_read_all();
-        __syncwarp();
-        int words;
-        if (kSubHdrWords + total <= kFdctStageWords) {
-            // ---- the usual case: the whole sub-image is assembled in the staging buffer and leaves with one bulk store ----
-            const int first = incl - cnt;
-            // header: everything in it is known before the walk (an EOB is coded unless position 63 is non-zero)
-            s_out[lane] = valid ? sub_hdr_pack(diff, (int)(~mask_hi >> 31), cnt, first) : 0u;
-            if (valid) walk_into(s_out + kSubHdrWords + first);
-            __syncwarp();
-            count_entries(kSubHdrWords, kSubHdrWords + total);
-            words = kSubHdrWords + total;
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_s2g(gsub, s_out, (uint32_t)((words + 3) & ~3) * 4u);
-        } else {
-            // ---- dense content (more than 30 non-zero levels per block on average): two pieces, lanes 0-15 (with the
-            //      headers), then lanes 16-31, whose lists start on the next 16-byte boundary (the bulk copy's granule);
-            //      half a sub-image always fits the buffer ----
-            const int half_a = __shfl_sync(0xffffffffu, incl, 15);  // entries of lanes 0-15
-            const int split = (half_a + 3) & ~3;                    // where the second piece's entries start
-            const int first = incl - cnt + (lane >= 16 ? split - half_a : 0);
-            s_out[lane] = valid ? sub_hdr_pack(diff, (int)(~mask_hi >> 31), cnt, first) : 0u;
-            if (valid && lane < 16) walk_into(s_out + kSubHdrWords + first);
-            __syncwarp();
-            count_entries(kSubHdrWords, kSubHdrWords + half_a);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(gsub, s_out, (uint32_t)(kSubHdrWords + split) * 4u);
-                bulk_wait_read_all();  // the second piece reuses the buffer
-            }
-            __syncwarp();
-            if (valid && lane >= 16) walk_into(s_out + (first - split));
-            __syncwarp();
-            count_entries(0, total - half_a);
-            words = kSubHdrWords + split + (total - half_a);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_s2g(gsub + kSubHdrWords + split, s_out, (uint32_t)((total - half_a + 3) & ~3) * 4u);
+            if (prev < 63) atomicAdd(&hist[0], 1u);
+            if (zrl) atomicAdd(&hist[0xf0], zrl);
         }
-        if (lane == 0) dir[((long long)f * images_cap + tile) * kDirPerTile + warp] = (unsigned)words;
+
+        // ---- the warp's sub-image leaves with one bulk store ----
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+            bulk_s2g(images + ((long long)f * images_cap + tile) * kTileImageWords + warp * kSubImageWords, img, kSubImageBytes);
     }
     // the stores only have to be done READING shared memory before the CTA retires; they complete on their own and the
     // kernel boundary orders them before K4a

@@ -15,7 +15,7 @@
 
 namespace h2j {
 
-struct HuffPair { int a, b; };  // {value, prob} or {code, length}
+struct __align__(8) HuffPair { int a, b; };  // {value, prob} or {code, length}
 
 // tools/microbench/k3_phases.cu: cycle stamps of one table's phases (thread 0 of the CTA that builds table 2 of frame 0)
 #ifdef H2J_K3_CLOCKS
@@ -25,103 +25,144 @@ __device__ long long g_k3_clocks[16];
 #define K3_STAMP(i) do { } while (0)
 #endif
 
-__device__ void av_qsort_pairs(HuffPair *p, int num)
+// ---- AV_QSORT (libavutil/qsort.h), replayed ---------------------------------------------------------------
+// The reference's sort is an explicit-stack quicksort: median of three, partition around the middle element, a shortcut
+// for ranges that turn out sorted, then one of the two remaining ranges goes on the stack and the loop continues with the
+// other.  It is not stable, and where equal counts / equal lengths end up decides the DHT bytes, so every comparison and
+// swap of it is reproduced.  What is NOT reproduced is the order in which the ranges are taken: the two ranges a
+// partition leaves are disjoint and nothing outside a range is read or written while it is being sorted, so they can be
+// sorted at the same time -- by two threads -- with the result the sequential order gives.  qsort_range() is the
+// reference's loop body for one range; qsort_replay() runs the ranges of one recursion depth side by side, a round per
+// depth (~2 log2 n rounds instead of ~n/2 partitions one after the other: 20 us -> ~2 us for an AC table of 60 symbols).
+constexpr int kQsortMaxRanges = 136;  // ranges of one depth: at most num / 2 + 1 with num <= 257
+
+__device__ __forceinline__ void qsort_range(HuffPair *p, int start, int end, unsigned short (*next)[2], int *n_next)
 {
-#define H2J_CMP(x, y) ((x)->b - (y)->b)
-#define H2J_SWAP(x, y) do { HuffPair t_ = (x); (x) = (y); (y) = t_; } while (0)
-    HuffPair *stack[64][2];
-    int sp = 1;
-    stack[0][0] = p;
-    stack[0][1] = p + num - 1;
-    while (sp) {
-        HuffPair *start = stack[--sp][0];
-        HuffPair *end = stack[sp][1];
-        while (start < end) {
-            if (start < end - 1) {
-                int checksort = 0;
-                HuffPair *right = end - 2;
-                HuffPair *left = start + 1;
-                HuffPair *mid = start + ((end - start) >> 1);
-                if (H2J_CMP(start, end) > 0) {
-                    if (H2J_CMP(end, mid) > 0) H2J_SWAP(*start, *mid);
-                    else H2J_SWAP(*start, *end);
-                } else {
-                    if (H2J_CMP(start, mid) > 0) H2J_SWAP(*start, *mid);
-                    else checksort = 1;
-                }
-                if (H2J_CMP(mid, end) > 0) {
-                    H2J_SWAP(*mid, *end);
-                    checksort = 0;
-                }
-                if (start == end - 2) break;
-                H2J_SWAP(end[-1], *mid);
-                // The two scans below visit the elements in the reference's order and stop where it stops; only the LOADS
-                // differ: four keys are requested at once (the walk is a chain of shared-memory round trips otherwise --
-                // this thread is the frame's critical path).  Reading past `right` / below `left` is harmless: the keys
-                // are only looked at under the reference's own bounds test, and the addresses stay inside the array
-                // (start <= left, right <= end - 2, elements up to p[num + 2] exist).
-                const int pivot = end[-1].b;  // end[-1] is not touched inside the partition loop
-                while (left <= right) {
-                    for (;;) {
-                        const int k0 = left[0].b, k1 = left[1].b, k2 = left[2].b, k3 = left[3].b;
-                        if (!(left <= right && k0 < pivot)) break;
-                        left++;
-                        if (!(left <= right && k1 < pivot)) break;
-                        left++;
-                        if (!(left <= right && k2 < pivot)) break;
-                        left++;
-                        if (!(left <= right && k3 < pivot)) break;
-                        left++;
-                    }
-                    for (;;) {
-                        HuffPair *r1 = right - 1 < start ? start : right - 1, *r2 = right - 2 < start ? start : right - 2,
-                                 *r3 = right - 3 < start ? start : right - 3;
-                        const int k0 = right[0].b, k1 = r1->b, k2 = r2->b, k3 = r3->b;
-                        if (!(left <= right && k0 > pivot)) break;
-                        right--;
-                        if (!(left <= right && k1 > pivot)) break;
-                        right--;
-                        if (!(left <= right && k2 > pivot)) break;
-                        right--;
-                        if (!(left <= right && k3 > pivot)) break;
-                        right--;
-                    }
-                    if (left <= right) {
-                        H2J_SWAP(*left, *right);
-                        left++;
-                        right--;
-                    }
-                }
-                H2J_SWAP(end[-1], *left);
-                if (checksort && (mid == left - 1 || mid == left)) {
-                    mid = start;
-                    while (mid < end && H2J_CMP(mid, mid + 1) <= 0) mid++;
-                    if (mid == end) break;
-                }
-                if (end - left < left - start) {
-                    stack[sp][0] = start;
-                    stack[sp++][1] = right;
-                    start = left + 1;
-                } else {
-                    stack[sp][0] = left + 1;
-                    stack[sp++][1] = end;
-                    end = right;
-                }
-            } else {
-                if (H2J_CMP(start, end) > 0) H2J_SWAP(*start, *end);
-                break;
-            }
+    if (start >= end - 1) {  // two elements
+        const HuffPair a = p[start], b = p[end];
+        if (a.b > b.b) { p[start] = b; p[end] = a; }
+        return;
+    }
+    int checksort = 0;
+    int right = end - 2, left = start + 1;
+    const int mid = start + ((end - start) >> 1);
+    HuffPair ps = p[start], pm = p[mid], pe = p[end];  // (start < mid < end: three different elements)
+    auto swp = [](HuffPair &x, HuffPair &y) { const HuffPair t = x; x = y; y = t; };
+    if (ps.b > pe.b) {
+        if (pe.b > pm.b) swp(ps, pm);
+        else swp(ps, pe);
+    } else {
+        if (ps.b > pm.b) swp(ps, pm);
+        else checksort = 1;
+    }
+    if (pm.b > pe.b) {
+        swp(pm, pe);
+        checksort = 0;
+    }
+    p[start] = ps;
+    p[end] = pe;
+    if (start == end - 2) {
+        p[mid] = pm;
+        return;
+    }
+    // SWAP(end[-1], *mid): the pivot waits at end - 1 (mid <= end - 2 here)
+    p[mid] = p[end - 1];
+    p[end - 1] = pm;
+    const int pivot = pm.b;
+    // The two scans visit the elements in the reference's order and stop where it stops; only the LOADS differ: four
+    // keys are requested at once (a scan is a chain of shared-memory round trips otherwise).  Keys past `right` / below
+    // `left` are only looked at under the reference's own bounds test, and the addresses stay inside the array
+    // (start <= left, right <= end - 2, elements up to p[num + 2] exist).
+    while (left <= right) {
+        for (;;) {
+            const int k0 = p[left].b, k1 = p[left + 1].b, k2 = p[left + 2].b, k3 = p[left + 3].b;
+            if (!(left <= right && k0 < pivot)) break;
+            left++;
+            if (!(left <= right && k1 < pivot)) break;
+            left++;
+            if (!(left <= right && k2 < pivot)) break;
+            left++;
+            if (!(left <= right && k3 < pivot)) break;
+            left++;
+        }
+        for (;;) {
+            const int k0 = p[right].b, k1 = p[max(right - 1, start)].b, k2 = p[max(right - 2, start)].b, k3 = p[max(right - 3, start)].b;
+            if (!(left <= right && k0 > pivot)) break;
+            right--;
+            if (!(left <= right && k1 > pivot)) break;
+            right--;
+            if (!(left <= right && k2 > pivot)) break;
+            right--;
+            if (!(left <= right && k3 > pivot)) break;
+            right--;
+        }
+        if (left <= right) {
+            const HuffPair x = p[left], y = p[right];
+            p[left] = y;
+            p[right] = x;
+            left++;
+            right--;
         }
     }
-#undef H2J_CMP
-#undef H2J_SWAP
+    {  // SWAP(end[-1], *left)
+        const HuffPair x = p[end - 1], y = p[left];
+        p[end - 1] = y;
+        p[left] = x;
+    }
+    if (checksort && (mid == left - 1 || mid == left)) {
+        int m = start;
+        while (m < end && p[m].b <= p[m + 1].b) m++;
+        if (m == end) return;
+    }
+    if (start < right) {
+        const int i = atomicAdd(n_next, 1);
+        next[i][0] = (unsigned short)start;
+        next[i][1] = (unsigned short)right;
+    }
+    if (left + 1 < end) {
+        const int i = atomicAdd(n_next, 1);
+        next[i][0] = (unsigned short)(left + 1);
+        next[i][1] = (unsigned short)end;
+    }
+}
+
+struct QsortRounds {
+    unsigned short range[2][kQsortMaxRanges][2];
+    int count[3];  // ranges of this round / the next one / the one after (being cleared)
+};
+
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(128) : "memory"); }
+
+// all kHuffGroup threads of the group call this; p[0 .. num + 2] must exist
+__device__ void qsort_replay(HuffPair *p, int num, QsortRounds *Q, int gt, int group)
+{
+    if (gt == 0) {
+        Q->range[0][0][0] = 0;
+        Q->range[0][0][1] = (unsigned short)(num - 1);
+        Q->count[0] = num > 1 ? 1 : 0;
+        Q->count[1] = 0;
+        Q->count[2] = 0;
+    }
+    group_sync(group);
+    // range i goes to thread (i % 4) * 32 + i / 4: the first ranges of a round land in different warps (threads of one warp
+    // that sort different ranges take turns at every divergent step)
+    const int my_first = ((gt & 31) << 2) | (gt >> 5);
+    for (int round = 0;; round++) {
+        const int n = Q->count[round % 3];
+        if (n == 0) break;
+        if (gt == 0) Q->count[(round + 2) % 3] = 0;
+        for (int i = my_first; i < n; i += kHuffGroup)
+            qsort_range(p, Q->range[round & 1][i][0], Q->range[round & 1][i][1], Q->range[(round + 1) & 1], &Q->count[(round + 1) % 3]);
+        group_sync(group);
+    }
 }
 
 constexpr int kPmMaxItems = 516;  // a level holds at most 257 + 258/2 items; rounded up
 struct HuffScratch {
-    HuffPair sorted[260];                        // {value, count}, then sorted by count
-    HuffPair distinct[260];                      // {value, code length}, then sorted by length
-    int prob[2][kPmMaxItems];
+    HuffPair sorted[264];                        // {value, count}, then sorted by count (+ room for the scans' look-ahead)
+    HuffPair distinct[264];                      // {value, code length}, then sorted by length
+    QsortRounds rounds;
+    __align__(8) int prob[2][kPmMaxItems];
     unsigned short leaves[17][kPmMaxItems + 2];  // leaves[t][p] = number of symbols among the first p items of level t
     int nl[17];                                  // symbols counted at each level by the back-trace
     unsigned char nbits_by_value[260];
@@ -133,7 +174,6 @@ struct HuffScratch {
 #endif
 };
 
-__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kHuffGroup) : "memory"); }
 
 // exclusive prefix sum of `v` over the 128 threads of a group; *total receives the group sum
 __device__ __forceinline__ int group_excl_scan(int v, int gt, int group, int *warp_tot, int *total)
@@ -173,8 +213,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
     const int size = nval + 1;
     group_sync(group);
     K3_STAMP(1);
-    if (gt == 0) av_qsort_pairs(S->sorted, size);
-    group_sync(group);
+    qsort_replay(S->sorted, size, &S->rounds, gt, group);
     K3_STAMP(2);
 
     // ---- ff_mjpegenc_huffman_compute_bits, max_length 16: levels 0..15 take symbols, level 16 only packages ----
@@ -188,15 +227,18 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
         const int *pp = S->prob[cur];
         int *np = S->prob[cur ^ 1];
         const int L = t < 16 ? size : 0, npk = n_prev >> 1;
+        // ranks by binary search with a fixed number of steps (the same for every thread) and no branch inside: a step is one
+        // shared-memory round trip, so a level costs log2 of them
+        const int span = 1 << (32 - __clz(max(max(L, npk), 1)));  // power of two above both list lengths
         for (int idx = gt; idx < L + npk; idx += kHuffGroup) {
             if (idx < L) {
                 // symbol idx: preceded by its idx predecessors and by every package whose sum is <= its count
                 const int key = S->sorted[idx].b;
-                int lo = 0, hi = npk;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (pp[2 * mid] + pp[2 * mid + 1] <= key) lo = mid + 1;
-                    else hi = mid;
+                int lo = 0;
+                for (int step = span >> 1; step; step >>= 1) {
+                    const int m = lo + step - 1;  // candidate: packages 0 .. m all have sums <= key?
+                    const int2 pr = *reinterpret_cast<const int2 *>(&pp[2 * max(min(m, npk - 1), 0)]);
+                    if (m < npk && pr.x + pr.y <= key) lo += step;
                 }
                 const int p = idx + lo;
                 np[p] = key;
@@ -204,12 +246,12 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
             } else {
                 // package m: preceded by its m predecessors and by every symbol whose count is < its sum
                 const int m = idx - L;
-                const int key = pp[2 * m] + pp[2 * m + 1];
-                int lo = 0, hi = L;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S->sorted[mid].b < key) lo = mid + 1;
-                    else hi = mid;
+                const int2 pr = *reinterpret_cast<const int2 *>(&pp[2 * m]);
+                const int key = pr.x + pr.y;
+                int lo = 0;
+                for (int step = span >> 1; step; step >>= 1) {
+                    const int c = lo + step - 1;
+                    if (c < L && S->sorted[max(min(c, L - 1), 0)].b < key) lo += step;
                 }
                 const int p = m + lo;
                 np[p] = key;
@@ -252,8 +294,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
     }
     group_sync(group);
     K3_STAMP(4);
-    if (gt == 0) av_qsort_pairs(S->distinct, nval);
-    group_sync(group);
+    qsort_replay(S->distinct, nval, &S->rounds, gt, group);
     K3_STAMP(5);
     // ---- BITS / HUFFVAL, then ff_mjpeg_build_huffman_codes ----
     for (int i = gt; i < 256; i += kHuffGroup) {
