@@ -4,19 +4,18 @@
 
 #include <cuda_runtime.h>
 
-#include <atomic>
 #include <cmath>
-#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "h2j_kernels.cuh"
+
+// h2j_host_copy.cpp: memcpy with non-temporal stores (plain memcpy where the CPU has no AVX2)
+extern "C" void h2j_stream_copy(void *dst, const void *src, size_t n);
 
 using namespace h2j;
 
@@ -410,12 +409,15 @@ struct DeviceGuard {
     DeviceGuard device_guard__((e)->s.device); \
     CU(e, device_guard__.err)
 
-// ---- staging copies of h2j_encode_frame, spread over a few host threads -----------------------------------------
-// One picture's planes go from the caller's (pageable) memory into pinned staging before they can be uploaded; a single
-// thread copies about 10 GB/s, which made that memcpy -- 0.3 ms for a 1080p frame -- three quarters of the whole call.
-// The copy is cut into pieces; the caller and up to three helper threads take pieces off a shared counter, and the
-// caller uploads every piece as soon as it and all pieces in front of it are in place.  The helpers are process-wide,
-// start with the first picture and sleep between pictures (after a short spin, so that back-to-back calls find them awake).
+// ---- staging copies of h2j_encode_frame -----------------------------------------------------------------------
+// One picture's planes go from the caller's (pageable) memory into pinned staging before they can be uploaded.  That
+// memcpy is the largest part of the call (0.26 of 0.35 ms for a 1080p frame: one thread copies ~12 GB/s on the pool's
+// hosts), so it is done with non-temporal stores (h2j_host_copy.cpp: the staging lines are next read by the DMA engine,
+// not by this core -- no read-for-ownership, +22 %), in pieces that are uploaded as soon as they are in place.
+// Measured and dropped: sharing the pieces with up to three helper threads (a process-wide pool taking pieces off an
+// atomic counter, spinning briefly between pictures) -- 0.45 ms instead of 0.35 on the GPU box and no gain in a host-only
+// loop either: the copy is bound by what one process gets out of memory here, and waking the helpers costs more than
+// they bring.
 struct CopyPiece {
     uint8_t *dst;
     const uint8_t *src;
@@ -425,113 +427,10 @@ struct CopyPiece {
 
 void copy_piece(const CopyPiece &c)
 {
-    if (c.src_stride == c.row_bytes && c.dst_pitch == c.row_bytes) memcpy(c.dst, c.src, (size_t)c.rows * c.row_bytes);
+    if (c.src_stride == c.row_bytes && c.dst_pitch == c.row_bytes) h2j_stream_copy(c.dst, c.src, (size_t)c.rows * c.row_bytes);
     else
-        for (int r = 0; r < c.rows; r++) memcpy(c.dst + (size_t)r * c.dst_pitch, c.src + (size_t)r * c.src_stride, c.row_bytes);
+        for (int r = 0; r < c.rows; r++) h2j_stream_copy(c.dst + (size_t)r * c.dst_pitch, c.src + (size_t)r * c.src_stride, (size_t)c.row_bytes);
 }
-
-class CopyPool {
-public:
-    static constexpr int kMaxPieces = 96;
-    static CopyPool &get()
-    {
-        static CopyPool *p = new CopyPool();  // never destroyed: its threads must not be torn down from a static destructor
-        return *p;
-    }
-    // Copies pieces[0..n) with the helpers; `uploaded(i)` is called on the calling thread, in order, once pieces 0..i are
-    // all in place.  Returns false (nothing done) when another picture is using the pool: the caller then copies alone.
-    template <typename F> bool run(const CopyPiece *pieces, int n, F &&uploaded)
-    {
-        std::unique_lock<std::mutex> own(owner_, std::try_to_lock);
-        if (!own.owns_lock() || n > kMaxPieces) return false;
-        start_helpers();
-        for (int i = 0; i < n; i++) done_[i].store(0, std::memory_order_relaxed);
-        pieces_ = pieces;
-        n_ = n;
-        next_.store(0, std::memory_order_relaxed);
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            generation_.fetch_add(1, std::memory_order_release);
-        }
-        cv_.notify_all();
-        int issued = 0;
-        auto issue_ready = [&] {
-            while (issued < n && done_[issued].load(std::memory_order_acquire)) uploaded(issued++);
-        };
-        for (;;) {
-            const int i = next_.fetch_add(1, std::memory_order_relaxed);
-            if (i >= n) break;
-            copy_piece(pieces[i]);
-            done_[i].store(1, std::memory_order_release);
-            issue_ready();
-        }
-        while (issued < n) {
-            issue_ready();
-            if (issued < n) cpu_relax();
-        }
-        // the helpers may still be looking at next_ / pieces_: wait until every one that joined this picture has left it
-        while (inside_.load(std::memory_order_acquire) != 0) cpu_relax();
-        n_ = 0;  // a helper that wakes up only now must not mistake the next picture's table for this one's
-        next_.store(1 << 30, std::memory_order_release);
-        return true;
-    }
-
-private:
-    static void cpu_relax()
-    {
-#if defined(__x86_64__) || defined(__i386__)
-        __builtin_ia32_pause();
-#else
-        std::this_thread::yield();
-#endif
-    }
-    void start_helpers()
-    {
-        if (started_) return;
-        started_ = true;
-        unsigned hw = std::thread::hardware_concurrency();
-        const int helpers = hw >= 8 ? 3 : (hw >= 4 ? 2 : (hw >= 2 ? 1 : 0));
-        for (int i = 0; i < helpers; i++) std::thread([this] { helper_main(); }).detach();
-    }
-    void helper_main()
-    {
-        unsigned long long seen = 0;
-        for (;;) {
-            // a short spin first: the next picture of a loop arrives within microseconds, a futex wake-up costs tens of them
-            unsigned long long g = generation_.load(std::memory_order_acquire);
-            for (int spin = 0; g == seen && spin < 4000; spin++) {
-                cpu_relax();
-                g = generation_.load(std::memory_order_acquire);
-            }
-            if (g == seen) {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
-                g = generation_.load(std::memory_order_acquire);
-            }
-            seen = g;
-            inside_.fetch_add(1, std::memory_order_acq_rel);
-            // (a helper that wakes up late finds next_ >= n_ -- possibly of a later picture -- and leaves at once; pieces_ and
-            // n_ are only read after a successful claim, and the owner waits for inside_ == 0 before it changes them)
-            for (;;) {
-                const int i = next_.fetch_add(1, std::memory_order_acq_rel);
-                if (i >= n_) break;
-                copy_piece(pieces_[i]);
-                done_[i].store(1, std::memory_order_release);
-            }
-            inside_.fetch_sub(1, std::memory_order_acq_rel);
-        }
-    }
-    std::mutex owner_;  // one picture at a time
-    std::mutex m_;
-    std::condition_variable cv_;
-    std::atomic<unsigned long long> generation_{0};
-    std::atomic<int> next_{1 << 30};
-    std::atomic<int> inside_{0};
-    std::atomic<unsigned char> done_[kMaxPieces];
-    const CopyPiece *pieces_ = nullptr;
-    int n_ = 0;
-    bool started_ = false;
-};
 
 int check_slot(h2j_encoder *e, int slot)
 {
@@ -935,8 +834,8 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
-    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels): copied in pieces by this
-    // thread and the copy helpers, every piece uploaded as soon as it is in place
+    // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels): copied in pieces, every
+    // piece uploaded as soon as it is in place, so that the DMA of one piece runs under the memcpy of the next
     ON_DEVICE(e);
     const size_t fb = tight_frame_bytes(width, height);
     const size_t dstride = align_up(fb, 256);
@@ -950,12 +849,13 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
     sl.n = 1;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
     {
-        CopyPiece pieces[CopyPool::kMaxPieces];
+        constexpr int kMaxPieces = 96;
+        CopyPiece pieces[kMaxPieces];
         int n_pieces = 0;
         auto plane = [&](const uint8_t *src, int stride, size_t off, int pw, int pitch, int ph) {
             // pieces of ~256 KiB, but never more than a third of the table per plane
             int rows_per_piece = std::max(1, (256 * 1024) / pitch);
-            rows_per_piece = std::max(rows_per_piece, (ph + CopyPool::kMaxPieces / 3 - 1) / (CopyPool::kMaxPieces / 3));
+            rows_per_piece = std::max(rows_per_piece, (ph + kMaxPieces / 3 - 1) / (kMaxPieces / 3));
             for (int r0 = 0; r0 < ph; r0 += rows_per_piece) {
                 const int r1 = std::min(ph, r0 + rows_per_piece);
                 CopyPiece &c = pieces[n_pieces++];
@@ -977,13 +877,9 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
             const cudaError_t ce = cudaMemcpyAsync(sl.d_frames + pieces[i].dev_off, sl.h_stage + pieces[i].dev_off, pieces[i].dev_bytes, cudaMemcpyHostToDevice, sl.stream);
             if (ce != cudaSuccess && up_err == cudaSuccess) up_err = ce;
         };
-        static const bool single_thread = getenv("H2J_STAGE_ONE_THREAD") != nullptr;  // measurement knob
-        if (single_thread || fb < 512 * 1024 || !CopyPool::get().run(pieces, n_pieces, upload)) {
-            // small pictures (waking helpers costs more than it saves), or the helpers are busy with another encoder's picture
-            for (int i = 0; i < n_pieces; i++) {
-                copy_piece(pieces[i]);
-                upload(i);
-            }
+        for (int i = 0; i < n_pieces; i++) {
+            copy_piece(pieces[i]);
+            upload(i);
         }
         CU(e, up_err);
     }

@@ -154,6 +154,9 @@ __device__ void qsort_replay(HuffPair *p, int num, QsortRounds *Q, int gt, int g
         for (int i = my_first; i < n; i += kHuffGroup)
             qsort_range(p, Q->range[round & 1][i][0], Q->range[round & 1][i][1], Q->range[(round + 1) & 1], &Q->count[(round + 1) % 3]);
         group_sync(group);
+#ifdef H2J_K3_CLOCKS
+        if (gt == 0) g_k3_clocks[15] = round + 1;  // rounds of the last sort
+#endif
     }
 }
 

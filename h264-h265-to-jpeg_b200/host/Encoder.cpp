@@ -62,14 +62,15 @@ bool save_jpeg(const char *filePath, const uint8_t *data, size_t n)
 void copy_planes(uint8_t *p, const H2JFrameView &f)
 {
     const int cw = (f.width + 1) >> 1, ch = (f.height + 1) >> 1;
-    if (f.linesize[0] == f.width) memcpy(p, f.data[0], (size_t)f.width * f.height);
+    // (h2j_stream_copy: non-temporal stores -- the staging lines are read next by the GPU's DMA engine, not by this core)
+    if (f.linesize[0] == f.width) h2j_stream_copy(p, f.data[0], (size_t)f.width * f.height);
     else
-        for (int r = 0; r < f.height; r++) memcpy(p + (size_t)r * f.width, f.data[0] + (size_t)r * f.linesize[0], f.width);
+        for (int r = 0; r < f.height; r++) h2j_stream_copy(p + (size_t)r * f.width, f.data[0] + (size_t)r * f.linesize[0], f.width);
     p += (size_t)f.width * f.height;
     for (int pl = 1; pl <= 2; pl++) {
-        if (f.linesize[pl] == cw) memcpy(p, f.data[pl], (size_t)cw * ch);
+        if (f.linesize[pl] == cw) h2j_stream_copy(p, f.data[pl], (size_t)cw * ch);
         else
-            for (int r = 0; r < ch; r++) memcpy(p + (size_t)r * cw, f.data[pl] + (size_t)r * f.linesize[pl], cw);
+            for (int r = 0; r < ch; r++) h2j_stream_copy(p + (size_t)r * cw, f.data[pl] + (size_t)r * f.linesize[pl], cw);
         p += (size_t)cw * ch;
     }
 }
@@ -199,7 +200,7 @@ void finish_job(Hub &H, DeviceCtx &D, int slot, Job *j, bool submitted)
     bool ok = submitted;
     if (ok) {
         int rc = h2j_collect(D.batch_box.enc, slot, j->out, j->out_bytes, offs.data(), st.data());
-        if (rc == H2J_ERR_BUFFER_TOO_SMALL) {  // (out_bytes = capacity x pictures rules it out; kept so that nothing is ever lost)
+        if (rc == H2J_ERR_BUFFER_TOO_SMALL) {  // more than 4 bits per pixel: the slot is still collectable, offs[n] is the size
             h2j_free_pinned(j->out);
             j->out_bytes = offs[n];
             j->out = static_cast<uint8_t *>(h2j_alloc_pinned(j->out_bytes));
@@ -258,9 +259,13 @@ void worker_main(Hub *Hp, DeviceCtx *Dp)
                 while (!running.empty()) finish_oldest();
             if (stale) drop_box(D.batch_box);
             bool ok = ensure_box(D.batch_box, D.device, H.range_mode, j->w, j->h, j->cap_frames, kSlotsPerDevice);
-            if (ok && j->out_bytes < D.batch_box.cap * (size_t)j->cap_frames) {
+            // pinned room for the batch's JPEGs: 4 bits per pixel to start with (camera pictures at the reference's settings
+            // come to about 1 bit); a batch that needs more is collected again into a buffer of exactly its size (finish_job)
+            size_t per_picture = (size_t)j->w * j->h / 2 + 65536;
+            if (per_picture > D.batch_box.cap) per_picture = D.batch_box.cap;
+            if (ok && j->out_bytes < per_picture * (size_t)j->cap_frames) {
                 if (j->out) h2j_free_pinned(j->out);
-                j->out_bytes = D.batch_box.cap * (size_t)j->cap_frames;
+                j->out_bytes = per_picture * (size_t)j->cap_frames;
                 j->out = static_cast<uint8_t *>(h2j_alloc_pinned(j->out_bytes));
                 if (!j->out) {
                     LOG("%s line=%d | pinned allocation of %zu bytes failed", __PRETTY_FUNCTION__, __LINE__, j->out_bytes);

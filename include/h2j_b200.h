@@ -145,6 +145,9 @@ int h2j_wait(h2j_encoder *e, int slot);
 /* Pinned host memory helpers so callers in any language can get full-speed copies. */
 void *h2j_alloc_pinned(size_t bytes);
 void h2j_free_pinned(void *p);
+/* memcpy for filling pinned staging that the GPU reads next: non-temporal stores where the CPU has AVX2 (no
+ * read-for-ownership of the destination, the caller's cache keeps its contents), plain memcpy otherwise. */
+void h2j_stream_copy(void *dst, const void *src, size_t n);
 
 /*
  * Standalone plane conversion (kernel 1 on its own): yuv420p limited -> yuvj420p full, with the encoder's

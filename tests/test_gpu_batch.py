@@ -97,3 +97,41 @@ def test_error_behaviour(orc):
         # the encoder stays usable afterwards
     with h2j_b200.Encoder(max_width=64, max_height=64, max_batch=1, n_slots=1) as e:
         assert e.yuv2jpeg(y, u, v) == orc.oracle_encode(y, u, v)[0]
+
+
+def test_collect_with_a_short_buffer_can_be_repeated(orc):
+    """h2j_collect with a caller buffer shorter than the batch: H2J_ERR_BUFFER_TOO_SMALL, the sizes are reported, nothing is
+    lost -- the same slot collects into a buffer of the reported size -- and a frame that outgrew max_jpeg_bytes comes back as
+    a zero-length entry with its status while its neighbours are delivered (strict=False)."""
+    import h2j_b200
+
+    w, h = 320, 192
+    planes = [orc.synth_planes(w, h, "textured", seed=70 + s, amp=20 + 10 * s) for s in range(3)]
+    frames = np.stack([orc.pack_i420(*p) for p in planes])
+    want = [orc.oracle_encode(*p)[0] for p in planes]
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=3, n_slots=1) as e:
+        e.submit_host(0, frames.ctypes.data, frames.shape[1], 3, w, h)
+        small = np.empty(1000, np.uint8)
+        with pytest.raises(h2j_b200.H2JError) as ei:
+            e.collect_into(0, small.ctypes.data, small.size)
+        assert ei.value.status == h2j_b200.ERR_BUFFER_TOO_SMALL
+        sizes = np.diff(ei.value.offsets)
+        assert [int(x) for x in sizes] == [len(j) for j in want]
+        big = np.empty(int(ei.value.offsets[-1]), np.uint8)
+        offs, st = e.collect_into(0, big.ctypes.data, big.size)
+        assert list(st) == [0, 0, 0]
+        for i in range(3):
+            assert big[int(offs[i]): int(offs[i + 1])].tobytes() == want[i]
+        with pytest.raises(h2j_b200.H2JError) as ei:  # now the slot is free
+            e.collect_into(0, big.ctypes.data, big.size)
+        assert ei.value.status == h2j_b200.ERR_BUSY
+    # one frame of three does not fit max_jpeg_bytes
+    noisy = orc.synth_planes(w, h, "noise", seed=5, amp=120)
+    frames2 = np.stack([orc.pack_i420(*planes[0]), orc.pack_i420(*noisy), orc.pack_i420(*planes[2])])
+    cap = max(len(want[0]), len(want[2])) + 64
+    assert len(orc.oracle_encode(*noisy)[0]) > cap
+    with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=3, n_slots=1, max_jpeg_bytes=cap) as e:
+        e.submit_host(0, frames2.ctypes.data, frames2.shape[1], 3, w, h)
+        res = e.collect(0, strict=False)
+        assert res.status[0] == 0 and res.status[2] == 0 and res.status[1] == h2j_b200.ERR_OUTPUT_TOO_SMALL
+        assert res.jpegs[0] == want[0] and res.jpegs[2] == want[2] and res.jpegs[1] == b""
