@@ -341,15 +341,50 @@ class Ctx:
         return [float(v) for v in g.tolist()]
 
 
-def rank_to_device(torch, local_rank, world):
-    """GPU of a rank.  With more GPUs visible than ranks the ranks are spread evenly over the ordinals (N=2 -> 0, 4; N=4 ->
-    0, 2, 4, 6 on an 8-GPU box) so that they do not crowd the PCIe switches / root ports of the low ordinals: the
-    host-to-host pass is bound by the host->device link.  H2J_BENCH_SPREAD=0 keeps rank i on GPU i."""
+def pick_devices(per_gpu_gbs, world):
+    """The `world` GPUs with the best host->device rate when every GPU of the box copies at once (ties: lower ordinal),
+    in ascending order."""
+    order = sorted(range(len(per_gpu_gbs)), key=lambda g: (-round(per_gpu_gbs[g], 0), g))
+    return sorted(order[:world])
+
+
+def device_plan(torch, local_rank, world):
+    """GPU of a rank, and every rank's host->device rate.  The host-to-host pass is bound by the host->device link, and
+    on the 8-GPU boxes of this pool the GPUs are not equal there: GPUs 0-3 share ~117 GB/s of host reads, GPUs 4-7 get 55
+    GB/s each, all eight together 24 + 36 GB/s (profiles/r2g_pcie_probe.jsonl), while `nvidia-smi topo -m` shows one flat
+    NUMA node (the VM hides the sockets).  So a multi-rank job asks the box: local rank 0 runs tools/microbench/pcie_probe
+    (plain pinned cudaMemcpyAsync on all GPUs at once, in a process of its own), a job with fewer ranks than visible GPUs
+    takes the GPUs with the best rates, and the host-to-host pass sizes the ranks' shards by their rates
+    (h2j_b200.weighted_shards).  H2J_BENCH_SPREAD=0 keeps rank i on GPU i with equal shards; if the probe is not there the
+    ranks are spread evenly over the ordinals.  Returns (device ordinal, description, rates of the ranks' GPUs or None)."""
     n = torch.cuda.device_count()
-    if n > world and os.environ.get("H2J_BENCH_SPREAD", "1") != "0":
-        step = n // world
-        return local_rank * step, f"spread: rank i on GPU {step} * i of {n} visible"
-    return local_rank, f"identity: rank i on GPU i of {n} visible"
+    if world <= 1 or n < world or os.environ.get("H2J_BENCH_SPREAD", "1") == "0":
+        return local_rank, f"identity: rank i on GPU i of {n} visible", None
+    share = os.path.join(tempfile.gettempdir(), f"h2j_bench_devices_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}.json")
+    if local_rank == 0:
+        plan, why = None, "unusable output"
+        try:
+            exe = os.path.join(ROOT, "tools", "microbench", "pcie_probe")
+            r = subprocess.run([exe, "all"], capture_output=True, text=True, timeout=120)
+            rates = json.loads(r.stdout.strip().splitlines()[-1])["h2d_gbs_per_gpu"]
+            if len(rates) == n and min(rates) > 0:
+                gpus = pick_devices(rates, world)
+                plan = {"gpus": gpus, "rates": [rates[g] for g in gpus], "how": f"probe: H2D GB/s per GPU with all {n} copying at once = {rates}"}
+        except Exception as ex:
+            why = str(ex)[:80]
+        if plan is None:
+            step = n // world
+            plan = {"gpus": [i * step for i in range(world)], "rates": None, "how": f"no probe ({why}): every {step}-th GPU of {n}"}
+        with open(share + ".tmp", "w") as f:
+            json.dump(plan, f)
+        os.replace(share + ".tmp", share)
+    t0 = time.time()
+    while not os.path.exists(share):
+        if time.time() - t0 > 180:
+            return local_rank, "identity: the device plan of local rank 0 never arrived", None
+        time.sleep(0.05)
+    plan = json.load(open(share))
+    return plan["gpus"][local_rank], f"rank i on GPU {plan['gpus']}[i] -- {plan['how']}", plan["rates"]
 
 
 def oracle_jpeg(frame_bytes, w, h):
@@ -453,7 +488,7 @@ def device_pass(cx, enc, streams, d_frames, stride, fb, F, SB, NS, w, h, steps, 
     return out
 
 
-def e2e_pass(cx, d_frames, stride, fb, F, ESB, ENS, w, h, steps, warmup, max_jpeg_bytes=0, sample=0):
+def e2e_pass(cx, d_frames, stride, fb, F, ESB, ENS, w, h, steps, warmup, max_jpeg_bytes=0, sample=0, job_frames=None):
     """Host-to-host through the C ABI: pinned I420 frames in (H2D every step), packed JPEG bytes out to pinned host
     memory (D2H every step); wall clock between device synchronisations, max over ranks.  After the timed region one more
     (untimed) step runs with `sample` frames of its first, middle and last sub-batch compared with the oracle."""
@@ -507,11 +542,13 @@ def e2e_pass(cx, d_frames, stride, fb, F, ESB, ENS, w, h, steps, warmup, max_jpe
     cx.barrier()
     dt_max = cx.max_over_ranks(dt)
     per_rank_s = cx.gather(dt)
-    res = {"value": cx.world * F * steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": cx.world * F * fb,
-           "d2h_bytes_per_step": cx.world * d2h[0] // max(1, steps), "timing": "wall clock between device synchronisations, max over ranks",
-           "sub_batch": ESB, "slots": ENS, "h2d_gbs": cx.world * F * fb * steps / dt_max / 1e9, "pinned_numa_node": numa.node,
+    job = job_frames if job_frames is not None else cx.world * F  # frames all ranks encode per step (F is THIS rank's share)
+    res = {"value": job * steps / dt_max, "unit": UNIT, "h2d_bytes_per_step": job * fb,
+           "d2h_bytes_per_step": int(sum(cx.gather(float(d2h[0])))) // max(1, steps), "timing": "wall clock between device synchronisations, max over ranks",
+           "sub_batch": ESB, "slots": ENS, "h2d_gbs": job * fb * steps / dt_max / 1e9, "pinned_numa_node": numa.node,
            "per_rank": {"ms_per_step": [round(1000 * x / steps, 3) for x in per_rank_s],
-                        "h2d_gbs": [round(F * fb * steps / x / 1e9, 2) for x in per_rank_s],
+                        "frames_per_step": [int(x) for x in cx.gather(float(F))],
+                        "h2d_gbs": [round(f_ * fb * steps / x / 1e9, 2) for f_, x in zip(cx.gather(float(F)), per_rank_s)],
                         "gpu": cx.gather(float(cx.dev.index))},
            "gpu_launches": enc.kernel_launches - launches0,
            "note": "host-pinned I420 in, packed JPEG bytes out to pinned host memory, every step; bound by the H2D copy "
@@ -707,7 +744,7 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the h2j_b200 path has no CPU fallback")
-    dev_index, mapping = rank_to_device(torch, local_rank, world)
+    dev_index, mapping, link_rates = device_plan(torch, local_rank, world)
     torch.cuda.set_device(dev_index)
     dev = torch.device("cuda", dev_index)
     if world > 1:
@@ -798,8 +835,23 @@ def run_ours(a):
     # ---- e2e: pinned host in, pinned host out ------------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        e2e = e2e_pass(cx, d_frames, stride, fb, F, a.e2e_sub_batch, a.e2e_slots, w, h, a.steps, a.warmup, sample=6)
+        # the job is still world*F frames sharded per image, but a rank's share follows its GPU's host->device rate where the
+        # box's links are not equal (a rank behind a slower link would otherwise set the time for everybody)
+        e_frames, e_F, shards = d_frames, F, None
+        if link_rates and os.environ.get("H2J_BENCH_BALANCE", "1") != "0" and max(link_rates) > 1.05 * min(link_rates):
+            shards = h2j_b200.weighted_shards(world * F, link_rates, a.e2e_sub_batch)
+            e_lo, e_hi = shards[rank]
+            e_F = e_hi - e_lo
+            if (e_lo, e_hi) != (lo, hi):
+                e_frames, _, _ = make_frames_torch(e_F, w, h, dev, seed0=e_lo)
+                torch.cuda.synchronize()
+        e2e = e2e_pass(cx, e_frames, stride, fb, e_F, a.e2e_sub_batch, a.e2e_slots, w, h, a.steps, a.warmup, sample=6, job_frames=world * F)
         e2e["rank_to_gpu"] = mapping
+        e2e["shards"] = {"frames_per_rank": [hi_ - lo_ for lo_, hi_ in shards], "weights_h2d_gbs": link_rates,
+                         "note": "per-image shards in proportion to each GPU's measured host->device rate"} if shards else "equal: F frames per rank"
+        if e_frames is not d_frames:
+            del e_frames
+            torch.cuda.empty_cache()
 
     # ---- the reference's own call shapes: one picture, and IDecoder::H265ToJpeg (rank 0) -------------
     single, dropin = None, None

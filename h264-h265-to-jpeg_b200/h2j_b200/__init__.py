@@ -156,6 +156,36 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def weighted_shards(n_items: int, weights: Sequence[float], granule: int = 1) -> List[Tuple[int, int]]:
+    """Per-image sharding with shares in proportion to `weights` -- e.g. each GPU's measured host->device rate when the
+    job is fed from host memory and the links of a box are not equal.  Returns one half-open range per rank: contiguous,
+    disjoint, covering [0, n_items), every share a multiple of `granule` (the submit size) except that the last rank
+    takes the remainder, no share empty while items are left.  Equal weights reproduce shard_range() for n_items divisible
+    by len(weights) * granule."""
+    k = len(weights)
+    if k < 1 or n_items < 0 or granule < 1 or any(not (w > 0) for w in weights):
+        raise ValueError(f"bad weighted shard request: n_items={n_items} weights={list(weights)} granule={granule}")
+    total = float(sum(weights))
+    units = n_items // granule  # whole granules to hand out; the remainder rides with the last rank
+    shares = [int(units * w / total) for w in weights]
+    # largest remainders first, so that the shares add up
+    order = sorted(range(k), key=lambda i: -(units * weights[i] / total - shares[i]))
+    for i in order[: units - sum(shares)]:
+        shares[i] += 1
+    if units >= k:  # nobody idle: take from the largest share
+        for i in range(k):
+            while shares[i] == 0:
+                j = max(range(k), key=lambda x: shares[x])
+                shares[j] -= 1
+                shares[i] += 1
+    out, lo = [], 0
+    for i, sh in enumerate(shares):
+        hi = lo + sh * granule + (n_items - units * granule if i == k - 1 else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 def sub_batches(lo: int, hi: int, max_batch: int) -> List[Tuple[int, int]]:
     """Cut a rank's range into submit-sized pieces (each at most `max_batch` frames), in order."""
     if max_batch < 1:

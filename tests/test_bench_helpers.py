@@ -66,7 +66,7 @@ def test_sample_indices_hold_first_last_and_stay_in_range():
         assert all(0 <= i < n for i in pick)
 
 
-def test_rank_to_device_spreads_only_when_gpus_are_left_over(monkeypatch):
+def test_device_plans(monkeypatch, tmp_path):
     import bench
 
     class FakeCuda:
@@ -80,9 +80,21 @@ def test_rank_to_device_spreads_only_when_gpus_are_left_over(monkeypatch):
         def __init__(self, n):
             self.cuda = FakeCuda(n)
 
-    assert [bench.rank_to_device(FakeTorch(8), r, 4)[0] for r in range(4)] == [0, 2, 4, 6]
-    assert [bench.rank_to_device(FakeTorch(8), r, 2)[0] for r in range(2)] == [0, 4]
-    assert [bench.rank_to_device(FakeTorch(8), r, 8)[0] for r in range(8)] == list(range(8))
-    assert [bench.rank_to_device(FakeTorch(2), r, 2)[0] for r in range(2)] == [0, 1]
+    # the measured rates of the pool's 8-GPU box: GPUs 4-7 are the good ones
+    rates = [23.6, 23.6, 23.6, 23.6, 36.1, 36.2, 36.2, 36.1]
+    assert bench.pick_devices(rates, 4) == [4, 5, 6, 7]
+    assert bench.pick_devices(rates, 2) == [4, 5]
+    assert bench.pick_devices([55.0] * 8, 4) == [0, 1, 2, 3]
+    # as many ranks as GPUs, one rank, or the knob: identity
+    assert bench.device_plan(FakeTorch(8), 0, 1)[0] == 0
     monkeypatch.setenv("H2J_BENCH_SPREAD", "0")
-    assert [bench.rank_to_device(FakeTorch(8), r, 2)[0] for r in range(2)] == [0, 1]
+    assert [bench.device_plan(FakeTorch(8), r, 2)[0] for r in range(2)] == [0, 1]
+    assert [bench.device_plan(FakeTorch(8), r, 8)[0] for r in range(8)] == list(range(8))
+    monkeypatch.delenv("H2J_BENCH_SPREAD")
+    # fewer ranks than GPUs, no usable probe here (no GPU): local rank 0 publishes the even spread, the others read it
+    monkeypatch.setattr(bench.tempfile, "gettempdir", lambda: str(tmp_path))
+    monkeypatch.setenv("MASTER_PORT", "29999")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))  # no pcie_probe binary under this root
+    assert bench.device_plan(FakeTorch(8), 0, 4)[0] == 0
+    assert [bench.device_plan(FakeTorch(8), r, 4)[0] for r in range(1, 4)] == [2, 4, 6]
+    assert bench.device_plan(FakeTorch(8), 3, 4)[2] is None  # no rates without a probe: equal shards

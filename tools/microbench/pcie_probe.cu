@@ -5,6 +5,8 @@
 //   wc       cudaHostAlloc(write-combined)       no CPU cache snooping on the read
 //   huge     mmap + MADV_HUGEPAGE + cudaHostRegister   2 MiB pages behind the IOMMU
 // Usage: pcie_probe [mb_per_copy=199] [copies=40] ; prints one JSON line per (subset, kind).
+//        pcie_probe all [mb_per_copy=64] [copies=12] ; ONE line: every visible GPU copying at once (what bench.py reads to
+//        decide which GPUs a job with fewer ranks than GPUs should use).
 #include <cuda_runtime.h>
 #include <sys/mman.h>
 
@@ -136,6 +138,14 @@ static void run_set(const std::vector<int> &devs, Kind kind, size_t bytes, int c
 
 int main(int argc, char **argv)
 {
+    if (argc > 1 && !strcmp(argv[1], "all")) {
+        int nd = 0;
+        CK(cudaGetDeviceCount(&nd));
+        std::vector<int> all;
+        for (int i = 0; i < nd; i++) all.push_back(i);
+        run_set(all, PINNED, (size_t)(argc > 2 ? atoi(argv[2]) : 64) * 1000 * 1000, argc > 3 ? atoi(argv[3]) : 12, false);
+        return 0;
+    }
     const size_t mb = argc > 1 ? (size_t)atoi(argv[1]) : 199;
     const int copies = argc > 2 ? atoi(argv[2]) : 40;
     int ndev = 0;
