@@ -108,3 +108,63 @@ def test_dropin_batch_scope_on_the_reference_fixtures(tmp_path):
     for out, name in zip(outs, names):
         key = name.replace(".", "_")
         assert hashlib.sha256(open(out, "rb").read()).hexdigest() == z[key + "_full_sha256"].tobytes().decode()
+
+
+def test_hub_uses_a_second_device_when_the_first_is_busy(orc, tmp_path):
+    """The host mirror spreads over the box by itself (h2j_host_configure(-1, ...), the default): inside a batch scope fed by
+    several caller threads the batches pile up while the first GPU is still coming up, a second device context is started,
+    and every file -- whichever GPU made it -- is the oracle's.  Needs two GPUs."""
+    import threading
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU: the hub has nothing to spread over")
+    lib = C.CDLL(HOST_SO)
+    lib.h2j_host_yuv2jpeg_file.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    lib.h2j_host_batch_end.argtypes = [C.POINTER(C.c_int)]
+    lib.h2j_host_configure.argtypes = [C.c_int, C.c_int]
+    lib.h2j_host_configure.restype = None
+    lib.h2j_host_configure(-1, 0)
+    w, h, per_thread, n_threads = 640, 368, 12, 4
+    planes = [orc.synth_planes(w, h, "textured", seed=900 + i, amp=20 + 3 * i) for i in range(6)]
+    want = [orc.oracle_encode(*p)[0] for p in planes]
+    assert lib.h2j_host_batch_begin(2) == 0
+    ok = []
+
+    def caller(t):
+        for i in range(per_thread):
+            y, u, v = planes[(t + i) % len(planes)]
+            out = str(tmp_path / f"t{t}_{i}.jpeg").encode()
+            ok.append(lib.h2j_host_yuv2jpeg_file(y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], w, h, 0, out))
+
+    threads = [threading.Thread(target=caller, args=(t,)) for t in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    failed = C.c_int(-1)
+    assert lib.h2j_host_batch_end(C.byref(failed)) == per_thread * n_threads and failed.value == 0 and all(ok)
+    assert lib.h2j_host_devices_in_use() >= 2
+    for t in range(n_threads):
+        for i in range(per_thread):
+            assert open(tmp_path / f"t{t}_{i}.jpeg", "rb").read() == want[(t + i) % len(planes)]
+    # the synchronous path from several threads at once: every call finds a device
+    outs = []
+
+    def sync_caller(t):
+        y, u, v = planes[t % len(planes)]
+        out = str(tmp_path / f"s{t}.jpeg")
+        for _ in range(5):
+            outs.append((t, lib.h2j_host_yuv2jpeg_file(y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], w, h, 0, out.encode())))
+
+    threads = [threading.Thread(target=sync_caller, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert len(outs) == 20 and all(r == 1 for _, r in outs)
+    for t in range(4):
+        assert open(tmp_path / f"s{t}.jpeg", "rb").read() == want[t % len(planes)]
+    lib.h2j_host_configure(0, 0)  # the other tests of this process expect device 0
