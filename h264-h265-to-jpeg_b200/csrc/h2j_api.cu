@@ -65,6 +65,7 @@ struct Slot {
     std::vector<cudaEvent_t> events;
     int timings_used = 0, events_used = 0;
     bool chain = false;  // the last thing enqueued was a timed kernel: its stop event is the next kernel's start
+    bool timing_failed = false;  // an event of this batch's brackets could not be created / recorded
 };
 
 }  // namespace
@@ -247,17 +248,27 @@ struct ScopedTiming {
     Slot &sl;
     bool on;
     int idx = -1;
+    // an event that cannot be created or recorded switches the brackets of this batch off (the kernels still run; the
+    // failure is remembered in the slot and reported by h2j_slot_kernel_ms)
     static int record(Slot &sl)
     {
         if (sl.events_used == (int)sl.events.size()) {
             cudaEvent_t ev;
-            cudaEventCreate(&ev);
+            if (cudaEventCreate(&ev) != cudaSuccess) {
+                cudaGetLastError();
+                sl.timing_failed = true;
+                return -1;
+            }
             sl.events.push_back(ev);
         }
-        cudaEventRecord(sl.events[sl.events_used], sl.stream);
+        if (cudaEventRecord(sl.events[sl.events_used], sl.stream) != cudaSuccess) {
+            cudaGetLastError();
+            sl.timing_failed = true;
+            return -1;
+        }
         return sl.events_used++;
     }
-    ScopedTiming(h2j_encoder *e, Slot &s, const char *name) : sl(s), on(e->s.profile != 0)
+    ScopedTiming(h2j_encoder *e, Slot &s, const char *name) : sl(s), on(e->s.profile != 0 && !s.timing_failed)
     {
         if (!on) return;
         if (sl.timings_used == (int)sl.timings.size()) sl.timings.push_back(KernelTiming{name, -1, -1});
@@ -268,8 +279,8 @@ struct ScopedTiming {
     ~ScopedTiming()
     {
         if (!on) return;
-        sl.timings[idx].stop = record(sl);
-        sl.chain = true;
+        sl.timings[idx].stop = sl.timing_failed ? -1 : record(sl);
+        sl.chain = !sl.timing_failed;
     }
 };
 
@@ -286,6 +297,7 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
     sl.timings_used = 0;
     sl.events_used = 0;
     sl.chain = false;
+    sl.timing_failed = false;
     CU(e, cudaMemsetAsync(sl.d_zero, 0, sl.zero_bytes, st));
     {
         ScopedTiming t(e, sl, "mbvar_kernel");
@@ -1035,12 +1047,15 @@ int h2j_slot_kernel_ms(h2j_encoder *e, int slot, const char **names, float *ms, 
     Slot &sl = e->slots[slot];
     ON_DEVICE(e);
     CU(e, cudaStreamSynchronize(sl.stream));
+    if (sl.timing_failed) return fail(e, H2J_ERR_CUDA, "a timing event of the slot's last batch could not be created or recorded");
     int n = 0;
-    for (int i = 0; i < sl.timings_used && n < cap; i++, n++) {
+    for (int i = 0; i < sl.timings_used && n < cap; i++) {
+        if (sl.timings[i].start < 0 || sl.timings[i].stop < 0) continue;
         float t = 0.f;
         CU(e, cudaEventElapsedTime(&t, sl.events[sl.timings[i].start], sl.events[sl.timings[i].stop]));
         if (names) names[n] = sl.timings[i].name;
         if (ms) ms[n] = t;
+        n++;
     }
     return n;
 }
