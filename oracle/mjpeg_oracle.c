@@ -650,14 +650,18 @@ long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const 
 {
     const int w = p->width, h = p->height;
     if (w <= 0 || h <= 0 || w > 65500 || h > 65500) return 0;
-    const int cw = w >> 1, ch = h >> 1; /* what load_input_picture copies for planes 1/2 */
+    const int fmt = p->chroma_format;
+    if (fmt < 0 || fmt > 2) return 0;
+    /* av_pix_fmt_get_chroma_sub_sample: yuvj420p (1,1), yuvj422p (1,0), yuvj444p (0,0) */
+    const int hshift = fmt == ORC_CHROMA_444 ? 0 : 1, vshift = fmt == ORC_CHROMA_420 ? 1 : 0;
+    const int cw = w >> hshift, ch = h >> vshift; /* what load_input_picture copies for planes 1/2 */
     if (cw <= 0 || ch <= 0) return 0;
     const int mbw = (w + 15) >> 4, mbh = (h + 15) >> 4;
     const char *comment = p->comment ? p->comment : "Lavc58.117.101";
 
     uint8_t *cy = NULL, *cu = NULL, *cv = NULL;
     if (p->range_mode == 1) { /* optional swscale-exact limited->full conversion in front */
-        const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
+        const int fcw = (w + (1 << hshift) - 1) >> hshift, fch = (h + (1 << vshift) - 1) >> vshift;
         cy = malloc((size_t)w * h); cu = malloc((size_t)fcw * fch); cv = malloc((size_t)fcw * fch);
         orc_range_luma(y, ys, cy, w, w, h);
         orc_range_chroma(u, us, cu, fcw, fcw, fch);
@@ -675,7 +679,20 @@ long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const 
     orc_build_matrices(qscale, intra_matrix, qmat16, bias16);
 
     /* ---- encode_thread / encode_mb: record symbols for every MCU ------------------------------ */
-    const long nblocks = (long)mbw * mbh * 6;
+    /* mpegvideo_enc.c encode_mb_internal numbers the blocks of a 16x16 macroblock: 0..3 luma (TL TR BL BR), then
+     *   4:2:0  4 Cb, 5 Cr
+     *   4:2:2  4 Cb top, 5 Cr top, 6 Cb bottom, 7 Cr bottom
+     *   4:4:4  4 Cb TL, 5 Cr TL, 6 Cb TR, 7 Cr TR, 8 Cb BL, 9 Cr BL, 10 Cb BR, 11 Cr BR
+     * and mjpegenc.c ff_mjpeg_encode_mb codes them in JPEG MCU order:
+     *   4:2:0  0 1 2 3 4 5                     (16x16 MCU, Y 2x2, Cb 1x1, Cr 1x1)
+     *   4:2:2  0 1 2 3 4 6 5 7                 (16x16 MCU, Y 2x2, Cb 1x2, Cr 1x2)
+     *   4:4:4  0 2 4 8 5 9, then 1 3 6 10 7 11 if 16*mb_x+8 < width   (two 8x16 MCUs, every component 1x2) */
+    static const int order420[6] = {0, 1, 2, 3, 4, 5};
+    static const int order422[8] = {0, 1, 2, 3, 4, 6, 5, 7};
+    static const int order444[12] = {0, 2, 4, 8, 5, 9, 1, 3, 6, 10, 7, 11};
+    const int *order = fmt == ORC_CHROMA_420 ? order420 : (fmt == ORC_CHROMA_422 ? order422 : order444);
+    const int per_mb = fmt == ORC_CHROMA_420 ? 6 : (fmt == ORC_CHROMA_422 ? 8 : 12);
+    const long nblocks = (long)mbw * mbh * per_mb;
     huffsym_t *hb = malloc(sizeof(huffsym_t) * (size_t)nblocks * 64 + 64);
     uint32_t hist[4][256];
     memset(hist, 0, sizeof hist);
@@ -684,16 +701,25 @@ long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const 
     long blk = 0;
     for (int my = 0; my < mbh; my++)
         for (int mx = 0; mx < mbw; mx++)
-            for (int n = 0; n < 6; n++, blk++) {
+            for (int k = 0; k < per_mb; k++) {
+                if (fmt == ORC_CHROMA_444 && k >= 6 && !(16 * mx + 8 < w)) break; /* no right half */
+                const int n = order[k];
                 int16_t b[64], zz[64];
                 const uint8_t *pl; int st, pw, ph, bx, by;
                 if (n < 4) { pl = y; st = ys; pw = w; ph = h; bx = mx * 16 + (n & 1) * 8; by = my * 16 + (n >> 1) * 8; }
-                else { pl = (n == 4) ? u : v; st = (n == 4) ? us : vs; pw = cw; ph = ch; bx = mx * 8; by = my * 8; }
+                else {
+                    pl = (n & 1) ? v : u; st = (n & 1) ? vs : us; pw = cw; ph = ch;
+                    const int pos = (n - 4) >> 1; /* which chroma block of the component inside the macroblock */
+                    if (fmt == ORC_CHROMA_420) { bx = mx * 8; by = my * 8; }
+                    else if (fmt == ORC_CHROMA_422) { bx = mx * 8; by = my * 16 + pos * 8; }
+                    else { bx = mx * 16 + (pos & 1) * 8; by = my * 16 + (pos >> 1) * 8; }
+                }
                 for (int r = 0; r < 8; r++)
                     for (int c = 0; c < 8; c++) b[r * 8 + c] = pad_px(pl, st, pw, ph, bx + c, by + r); /* get_pixels */
                 orc_fdct_sse2(b);
                 int last_index = orc_quantize(b, zz, qmat16, bias16);
                 if (dbg && dbg->coefs) memcpy(dbg->coefs + blk * 64, zz, sizeof zz);
+                blk++;
                 /* record_block() */
                 int component = (n <= 3 ? 0 : (n & 1) + 1);
                 int table_id = (n <= 3 ? 0 : 1);
@@ -758,9 +784,13 @@ long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const 
     bw_put(&bw, 16, h);
     bw_put(&bw, 16, w);
     bw_put(&bw, 8, 3);
-    bw_put(&bw, 8, 1); bw_put(&bw, 4, 2); bw_put(&bw, 4, 2); bw_put(&bw, 8, 0);
-    bw_put(&bw, 8, 2); bw_put(&bw, 4, 1); bw_put(&bw, 4, 1); bw_put(&bw, 8, 0);
-    bw_put(&bw, 8, 3); bw_put(&bw, 4, 1); bw_put(&bw, 4, 1); bw_put(&bw, 8, 0);
+    /* mjpegenc_common.c ff_mjpeg_init_hvsample: 4:4:4 is coded with every component at h = 1, v = 2 (8x16 MCUs), the
+     * others with luma at 2x2 and chroma at (2 >> chroma shift) */
+    const int hs0 = fmt == ORC_CHROMA_444 ? 1 : 2, vs0 = 2;
+    const int hsc = fmt == ORC_CHROMA_444 ? 1 : 2 >> hshift, vsc = fmt == ORC_CHROMA_444 ? 2 : 2 >> vshift;
+    bw_put(&bw, 8, 1); bw_put(&bw, 4, hs0); bw_put(&bw, 4, vs0); bw_put(&bw, 8, 0);
+    bw_put(&bw, 8, 2); bw_put(&bw, 4, hsc); bw_put(&bw, 4, vsc); bw_put(&bw, 8, 0);
+    bw_put(&bw, 8, 3); bw_put(&bw, 4, hsc); bw_put(&bw, 4, vsc); bw_put(&bw, 8, 0);
     bw_marker(&bw, M_SOS);
     bw_put(&bw, 16, 12);
     bw_put(&bw, 8, 3);
@@ -802,7 +832,8 @@ long orc_encode_frame(const uint8_t *y, int ys, const uint8_t *u, int us, const 
     bw_byte(&bw, M_EOI);
 
     if (dbg) {
-        dbg->qscale = qscale; dbg->lambda = lambda; dbg->mb_var_sum = var; dbg->mcu_w = mbw; dbg->mcu_h = mbh;
+        dbg->qscale = qscale; dbg->lambda = lambda; dbg->mb_var_sum = var;
+        dbg->mcu_w = fmt == ORC_CHROMA_444 ? (w + 7) >> 3 : mbw; dbg->mcu_h = mbh;
         memcpy(dbg->intra_matrix, intra_matrix, 64);
         memcpy(dbg->qmat16, qmat16, sizeof qmat16);
         memcpy(dbg->bias16, bias16, sizeof bias16);
@@ -900,6 +931,7 @@ long orc_jpeg_decode_coefs(const uint8_t *jpeg, long n, int16_t *out, long cap_b
     memset(tabs, 0, sizeof tabs);
     long i = 2;
     int w = 0, h = 0;
+    int hv[3][2] = {{0, 0}, {0, 0}, {0, 0}}; /* sampling factors (h, v) of the three components */
     if (n < 4 || jpeg[0] != 0xff || jpeg[1] != 0xd8) return -1;
     while (i + 4 <= n) {
         if (jpeg[i] != 0xff) return -2;
@@ -929,7 +961,9 @@ long orc_jpeg_decode_coefs(const uint8_t *jpeg, long n, int16_t *out, long cap_b
         } else if (m == 0xc0) {
             h = (seg[1] << 8) | seg[2];
             w = (seg[3] << 8) | seg[4];
-            if (seg[5] != 3 || seg[7] != 0x22 || seg[10] != 0x11 || seg[13] != 0x11) return -4;
+            if (seg[5] != 3) return -4;
+            for (int c = 0; c < 3; c++) { hv[c][0] = seg[7 + 3 * c] >> 4; hv[c][1] = seg[7 + 3 * c] & 15; }
+            if (hv[1][0] != hv[2][0] || hv[1][1] != hv[2][1] || hv[0][1] != 2) return -4;
         } else if (m == 0xda) {
             i += 2 + L;
             break;
@@ -937,13 +971,16 @@ long orc_jpeg_decode_coefs(const uint8_t *jpeg, long n, int16_t *out, long cap_b
         i += 2 + L;
     }
     if (!w || !h) return -5;
-    const int mbw = (w + 15) >> 4, mbh = (h + 15) >> 4;
-    const long nblk = (long)mbw * mbh * 6;
-    if (nblk > cap_blocks) return -6;
+    /* blocks of an MCU in scan order: h*v of every component; MCU = (8 * hmax) x (8 * vmax) pixels */
+    const int per_mcu = hv[0][0] * hv[0][1] + 2 * hv[1][0] * hv[1][1];
+    const int mbw = (w + 8 * hv[0][0] - 1) / (8 * hv[0][0]), mbh = (h + 15) >> 4;
+    const long nblk = (long)mbw * mbh * per_mcu;
+    if (per_mcu <= 0 || per_mcu > 12 || nblk > cap_blocks) return -6;
+    const int n_luma = hv[0][0] * hv[0][1], n_cb = hv[1][0] * hv[1][1];
     dec_bits_t b = {jpeg + i, jpeg + n, 0, 0, 0, 0};
     int pred[3] = {128, 128, 128}; /* the encoder's last_dc starts at 128 (level shift folded into DC) */
     for (long blk = 0; blk < nblk; blk++) {
-        const int nn = (int)(blk % 6), comp = nn < 4 ? 0 : nn - 3, th = nn < 4 ? 0 : 1;
+        const int nn = (int)(blk % per_mcu), comp = nn < n_luma ? 0 : (nn < n_luma + n_cb ? 1 : 2), th = comp ? 1 : 0;
         int16_t *o = out + blk * 64;
         memset(o, 0, 128);
         int s = dec_sym(&b, &tabs[0][th]);

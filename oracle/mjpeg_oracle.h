@@ -16,7 +16,13 @@ typedef struct orc_params {
     int range_mode;      /* 0: planes used as they are (what reference src/Encoder.cpp does);
                             1: swscale-exact yuv420p(limited) -> yuvj420p(full) first */
     const char *comment; /* COM payload; NULL = "Lavc58.117.101" (the x86_64_shared build) */
+    int chroma_format;   /* 0: 4:2:0 (yuvj420p, what reference src/Encoder.cpp:162 opens); 1: 4:2:2 (yuvj422p); 2: 4:4:4
+                            (yuvj444p) -- the same libavcodec encoder at its other MCU geometries */
 } orc_params;
+
+#define ORC_CHROMA_420 0
+#define ORC_CHROMA_422 1
+#define ORC_CHROMA_444 2
 
 typedef struct orc_debug {
     int qscale;
@@ -32,8 +38,9 @@ typedef struct orc_debug {
     int nvals[4];
     int64_t scan_bits;          /* entropy coded bits before the 1-padding */
     int header_bytes;           /* SOI .. end of SOS */
-    int16_t *coefs;             /* optional, caller-allocated [mcu_w*mcu_h*6*64]: quantised levels in
-                                   ZIGZAG order per block, blocks in MCU order Y0 Y1 Y2 Y3 Cb Cr */
+    int16_t *coefs;             /* optional, caller-allocated [mcu_w*mcu_h*blocks_per_mcu*64]: quantised levels in
+                                   ZIGZAG order per block, blocks in coding order (4:2:0: Y0 Y1 Y2 Y3 Cb Cr per 16x16 MCU;
+                                   4:2:2: Y0 Y1 Y2 Y3 Cb0 Cb1 Cr0 Cr1 per 16x16 MCU; 4:4:4: Y0 Y1 Cb0 Cb1 Cr0 Cr1 per 8x16 MCU) */
 } orc_debug;
 
 /* ff_fdct_sse2 restated (in place, natural order). */

@@ -23,6 +23,7 @@ extern "C" {
 #include "libavcodec/avdct.h"
 #include "libswscale/swscale.h"
 #include "libavutil/imgutils.h"
+#include "libavutil/pixdesc.h"
 }
 
 namespace {
@@ -277,6 +278,58 @@ int ref_h265_loop(const char *in_path, const char *out_prefix, int n_calls, int 
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     return ok;
+}
+
+// libavcodec's mjpeg encoder opened the way reference src/Encoder.cpp:158-204 opens it -- codec parameters (codec id, type,
+// format, size) -> context, time_base 1/25, every other option at its default, ONE frame sent, one packet received -- but for a
+// pixel format of the caller's choice.  The reference hard-codes AV_PIX_FMT_YUVJ420P (src/Encoder.cpp:162); this entry pins the
+// oracle's 4:2:2 / 4:4:4 modes (the same encoder at other MCU geometries) against the same library.  The
+// raw "mjpeg" muxer the reference writes through passes the packet bytes on unchanged, so the packet IS the file.
+// planes: y w x h; u, v (w >> hshift) x (h >> vshift) rounded up, tight or strided.  Returns the size, 0 on failure, -needed.
+long ref_mjpeg_encode_fmt(const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs, int w, int h, int pix_fmt,
+                          uint8_t *out, long cap)
+{
+    StdoutSilencer s(true);
+    AVCodec *codec = avcodec_find_encoder(AV_CODEC_ID_MJPEG);
+    if (!codec) return 0;
+    AVCodecParameters *par = avcodec_parameters_alloc();
+    AVCodecContext *cc = avcodec_alloc_context3(codec);
+    AVFrame *f = av_frame_alloc();
+    AVPacket *pkt = av_packet_alloc();
+    long ret = 0;
+    do {
+        if (!par || !cc || !f || !pkt) break;
+        par->codec_id = AV_CODEC_ID_MJPEG;
+        par->codec_type = AVMEDIA_TYPE_VIDEO;
+        par->format = pix_fmt;
+        par->width = w;
+        par->height = h;
+        if (avcodec_parameters_to_context(cc, par) < 0) break;
+        cc->time_base = (AVRational){1, 25};
+        if (avcodec_open2(cc, codec, nullptr) < 0) break;
+        f->width = w;
+        f->height = h;
+        f->format = pix_fmt;
+        f->pts = AV_NOPTS_VALUE;
+        if (av_frame_get_buffer(f, 32) < 0) break;
+        int hs = 0, vsft = 0;
+        av_pix_fmt_get_chroma_sub_sample((AVPixelFormat)pix_fmt, &hs, &vsft);
+        const int cw = (w + (1 << hs) - 1) >> hs, ch = (h + (1 << vsft) - 1) >> vsft;
+        for (int r = 0; r < h; r++) memcpy(f->data[0] + (size_t)r * f->linesize[0], y + (size_t)r * ys, w);
+        for (int r = 0; r < ch; r++) {
+            memcpy(f->data[1] + (size_t)r * f->linesize[1], u + (size_t)r * us, cw);
+            memcpy(f->data[2] + (size_t)r * f->linesize[2], v + (size_t)r * vs, cw);
+        }
+        if (avcodec_send_frame(cc, f) < 0) break;
+        if (avcodec_receive_packet(cc, pkt) < 0) break;
+        ret = pkt->size > cap ? -(long)pkt->size : pkt->size;
+        if (ret > 0) memcpy(out, pkt->data, pkt->size);
+    } while (0);
+    if (pkt) av_packet_free(&pkt);
+    if (f) av_frame_free(&f);
+    if (cc) avcodec_free_context(&cc);
+    if (par) avcodec_parameters_free(&par);
+    return ret;
 }
 
 const char *ref_version(void) { return LIBAVCODEC_IDENT; }

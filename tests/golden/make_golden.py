@@ -12,6 +12,9 @@
                        ff_fdct_sse2) makes of them
   ratecontrol.json     (mb_var_sum, qscale) pairs observed from the reference around every qscale threshold
   swscale_lut.npz      libswscale yuv420p -> yuvj420p mapping of all 256 values (luma, chroma)
+  golden_frames_fmt.json   the same encoder at 4:2:2 and 4:4:4: sha256 / size of what the libavcodec the
+                       reference vendors makes of integer-generated yuvj422p / yuvj444p frames, opened the way the reference
+                       opens it (oracle/ref_harness.cpp ref_mjpeg_encode_fmt).  `python make_golden.py formats` writes only this.
 """
 import hashlib
 import json
@@ -37,6 +40,27 @@ FRAME_CASES = [  # (w, h, seed, amp)
 
 def sha(b):
     return hashlib.sha256(b).hexdigest()
+
+
+FMT_CASES = [  # (w, h, seed, amp)
+    (16, 16, 1, 10), (2, 2, 2, 60), (17, 17, 3, 30), (33, 47, 4, 8), (64, 64, 5, 100), (131, 77, 6, 20), (322, 242, 7, 12),
+    (641, 479, 8, 40), (1280, 720, 9, 6), (1920, 1080, 10, 10), (1918, 1078, 11, 10), (8, 16, 12, 50), (9, 31, 13, 50), (24, 40, 14, 127),
+]
+
+
+def main_formats():
+    R = orc.reference()
+    frames = []
+    for fmt in (orc.CHROMA_422, orc.CHROMA_444):
+        for (w, h, seed, amp) in FMT_CASES:
+            y, u, v = orc.golden_planes_fmt(w, h, seed, amp, fmt)
+            j = orc.reference_encode_fmt(y, u, v, fmt)
+            frames.append({"chroma_format": fmt, "w": w, "h": h, "seed": seed, "amp": amp, "size": len(j), "sha256": sha(j),
+                           "planes_sha256": sha(y.tobytes() + u.tobytes() + v.tobytes())})
+            print("fmt", fmt, w, h, seed, amp, len(j))
+    json.dump({"generator": "tests/golden/make_golden.py formats", "reference": R.ref_version().decode(),
+               "pix_fmt": {"1": "yuvj422p", "2": "yuvj444p"}, "frames": frames},
+              open(os.path.join(HERE, "golden_frames_fmt.json"), "w"), indent=1)
 
 
 def main():
@@ -170,4 +194,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "formats":
+        main_formats()
+    else:
+        main()
+        main_formats()

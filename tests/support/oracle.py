@@ -23,7 +23,26 @@ MPEG1_INTRA = np.array([8, 16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 3
 
 class Params(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("pts", C.c_int64), ("fixed_qscale", C.c_int), ("range_mode", C.c_int),
-                ("comment", C.c_char_p)]
+                ("comment", C.c_char_p), ("chroma_format", C.c_int)]
+
+
+CHROMA_420, CHROMA_422, CHROMA_444 = 0, 1, 2
+PIX_FMT_OF = {CHROMA_420: 12, CHROMA_422: 13, CHROMA_444: 14}  # AV_PIX_FMT_YUVJ420P / YUVJ422P / YUVJ444P
+
+
+def chroma_shape(w, h, chroma_format):
+    """(rows, columns) of a chroma plane as the decoder hands it over: ceil(h / 2^vshift) x ceil(w / 2^hshift)"""
+    hs = 0 if chroma_format == CHROMA_444 else 1
+    vs = 1 if chroma_format == CHROMA_420 else 0
+    return (h + (1 << vs) - 1) >> vs, (w + (1 << hs) - 1) >> hs
+
+
+def blocks_of(w, h, chroma_format):
+    """number of 8x8 blocks the encoder codes"""
+    mh = (h + 15) // 16
+    if chroma_format == CHROMA_444:
+        return ((w + 7) // 8) * mh * 6
+    return ((w + 15) // 16) * mh * (6 if chroma_format == CHROMA_420 else 8)
 
 
 class Debug(C.Structure):
@@ -82,19 +101,21 @@ def reference() -> C.CDLL:
         lib.ref_fdct.argtypes = [vp, ci]
         lib.ref_sws_limited_to_full.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
         lib.ref_version.restype = C.c_char_p
+        lib.ref_mjpeg_encode_fmt.restype = C.c_long
+        lib.ref_mjpeg_encode_fmt.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, C.c_long]
         _ref = lib
     return _ref
 
 
-def oracle_encode(y, u, v, fixed_qscale=0, range_mode=0, comment=None, want_coefs=False, pts=NOPTS):
+def oracle_encode(y, u, v, fixed_qscale=0, range_mode=0, comment=None, want_coefs=False, pts=NOPTS, chroma_format=0):
     """Returns (jpeg bytes, Debug, coefs or None)."""
     h, w = y.shape
     lib = oracle()
-    p = Params(w, h, pts, fixed_qscale, range_mode, comment)
+    p = Params(w, h, pts, fixed_qscale, range_mode, comment, chroma_format)
     d = Debug()
     coefs = None
     if want_coefs:
-        nblk = ((w + 15) // 16) * ((h + 15) // 16) * 6
+        nblk = blocks_of(w, h, chroma_format)
         coefs = np.zeros((nblk, 64), np.int16)
         d.coefs = coefs.ctypes.data
     cap = w * h * 4 + 65536
@@ -113,6 +134,26 @@ def reference_encode(y, u, v, pts=NOPTS, pix_fmt=0) -> bytes:
                                  pix_fmt, out.ctypes.data, cap)
     assert n > 0, n
     return out[:n].tobytes()
+
+
+def reference_encode_fmt(y, u, v, chroma_format) -> bytes:
+    """libavcodec's mjpeg encoder opened as the reference opens it, at another chroma format (oracle/ref_harness.cpp)."""
+    h, w = y.shape
+    cap = 8 * 1024 * 1024
+    out = np.empty(cap, np.uint8)
+    n = reference().ref_mjpeg_encode_fmt(y.ctypes.data, y.strides[0], u.ctypes.data, u.strides[0], v.ctypes.data, v.strides[0], w, h,
+                                         PIX_FMT_OF[chroma_format], out.ctypes.data, cap)
+    assert n > 0, n
+    return out[:n].tobytes()
+
+
+def synth_planes_fmt(w, h, chroma_format, kind="textured", seed=0, amp=40):
+    """synth_planes with chroma planes of the given format's size"""
+    y, _, _ = synth_planes(w, h, kind, seed=seed, amp=amp)
+    ch, cw = chroma_shape(w, h, chroma_format)
+    cy, _, _ = synth_planes(cw, ch, kind, seed=seed + 1000, amp=max(1, amp // 2))
+    cz, _, _ = synth_planes(cw, ch, kind, seed=seed + 2000, amp=max(1, amp // 2))
+    return y, cy, cz
 
 
 def synth_planes(w, h, kind="textured", seed=0, amp=40):
@@ -163,6 +204,21 @@ def golden_planes(w, h, seed, amp):
     return plane(h, w, amp), plane(ch, cw, max(1, amp // 2)), plane(ch, cw, max(1, amp // 2))
 
 
+def golden_planes_fmt(w, h, seed, amp, chroma_format):
+    """golden_planes() with chroma planes of the given format's size (integer-only, platform independent)."""
+    rng = np.random.default_rng(seed + 7919 * (chroma_format + 1))
+    ch, cw = chroma_shape(w, h, chroma_format)
+
+    def plane(hh, ww, a):
+        blocks = rng.integers(32, 224, ((hh + 7) // 8, (ww + 7) // 8), dtype=np.int64)
+        base = np.kron(blocks, np.ones((8, 8), dtype=np.int64))[:hh, :ww]
+        walk = np.cumsum(rng.integers(-a, a + 1, (hh, ww), dtype=np.int64), axis=1) // 4
+        tex = rng.integers(-a, a + 1, (hh, ww), dtype=np.int64)
+        return np.clip(base + walk + tex, 0, 255).astype(np.uint8)
+
+    return plane(h, w, amp), plane(ch, cw, max(1, amp // 2)), plane(ch, cw, max(1, amp // 2))
+
+
 def decode_coefs(jpeg: bytes):
     """Independent baseline entropy decode (oracle/mjpeg_oracle.c orc_jpeg_decode_coefs).
     Returns (levels[n_blocks, 64] zigzag, info = [w, h, n_ff00, scan_bytes])."""
@@ -174,7 +230,9 @@ def decode_coefs(jpeg: bytes):
     i = jpeg.find(b"\xff\xc0")
     h = (jpeg[i + 5] << 8) | jpeg[i + 6]
     w = (jpeg[i + 7] << 8) | jpeg[i + 8]
-    nblk = ((w + 15) // 16) * ((h + 15) // 16) * 6
+    hv = [(jpeg[i + 11 + 3 * c] >> 4, jpeg[i + 11 + 3 * c] & 15) for c in range(3)]
+    per_mcu = hv[0][0] * hv[0][1] + 2 * hv[1][0] * hv[1][1]
+    nblk = ((w + 8 * hv[0][0] - 1) // (8 * hv[0][0])) * ((h + 15) // 16) * per_mcu
     out = np.zeros((nblk, 64), np.int16)
     info = np.zeros(4, np.int64)
     n = lib.orc_jpeg_decode_coefs(jb.ctypes.data, len(jpeg), out.ctypes.data, nblk, info.ctypes.data)

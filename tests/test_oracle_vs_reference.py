@@ -79,3 +79,18 @@ def test_range_conversion_matches_libswscale(orc):
             lib.orc_range_chroma(u.ctypes.data, cw, mu.ctypes.data, cw, cw, ch)
             lib.orc_range_chroma(v.ctypes.data, cw, mv.ctypes.data, cw, cw, ch)
             assert (my == oy).all() and (mu == ou).all() and (mv == ov).all()
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_oracle_matches_libavcodec_at_422_and_444(orc, fmt):
+    """Row f3, live: libavcodec's mjpeg encoder opened as reference src/Encoder.cpp:158-204 opens it but as yuvj422p / yuvj444p
+    (the reference itself hard-codes yuvj420p, :162) against the oracle's chroma_format modes, byte for byte."""
+    cases = [(64, 48, "textured", 40), (16, 16, "noise", 100), (17, 17, "noise", 60), (33, 47, "blocks", 30), (131, 77, "textured", 80),
+             (322, 242, "textured", 40), (641, 479, "noise", 20), (8, 16, "noise", 50), (9, 16, "noise", 50), (24, 40, "textured", 30),
+             (1280, 720, "textured", 30), (2, 2, "noise", 100), (25, 9, "binary", 0), (1918, 1078, "textured", 25)]
+    for i, (w, h, kind, amp) in enumerate(cases):
+        y, u, v = orc.synth_planes_fmt(w, h, fmt, kind, seed=50 + i, amp=amp)
+        assert orc.oracle_encode(y, u, v, chroma_format=fmt)[0] == orc.reference_encode_fmt(y, u, v, fmt), (fmt, w, h, kind)
+    # 4:2:0 through the same entry is the reference's own path
+    y, u, v = orc.synth_planes(322, 242, "textured", seed=3)
+    assert orc.reference_encode_fmt(y, u, v, 0) == orc.reference_encode(y, u, v)
