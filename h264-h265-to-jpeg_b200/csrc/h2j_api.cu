@@ -165,22 +165,30 @@ uint8_t range_lut_value(int s, bool chroma)  // libswscale lumRangeToJpeg_c / ch
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-size_t tight_frame_bytes(int w, int h) { return (size_t)w * h + 2 * (size_t)((w + 1) >> 1) * ((h + 1) >> 1); }
+// chroma plane of a w x h frame as the decoder hands it over: ceil-divided by the format's subsampling
+int chroma_w(int w, int fmt) { return (w + (1 << fmt_hshift(fmt)) - 1) >> fmt_hshift(fmt); }
+int chroma_h(int h, int fmt) { return (h + (1 << fmt_vshift(fmt)) - 1) >> fmt_vshift(fmt); }
+size_t tight_frame_bytes(int w, int h, int fmt) { return (size_t)w * h + 2 * (size_t)chroma_w(w, fmt) * chroma_h(h, fmt); }
 
 int make_layout(h2j_encoder *e, const uint8_t *base, size_t frame_stride, int w, int h, FrameLayout *L)
 {
     if (w < 2 || h < 2 || w > 65500 || h > 65500) return fail(e, H2J_ERR_UNSUPPORTED, "unsupported frame size %dx%d", w, h);
     if (w > e->s.max_width || h > e->s.max_height)
         return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum %dx%d", w, h, e->s.max_width, e->s.max_height);
-    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
-    L->w = w; L->h = h; L->cw = w >> 1; L->ch = h >> 1;
+    const int fmt = e->s.chroma_format;
+    const int fcw = chroma_w(w, fmt), fch = chroma_h(h, fmt);
+    L->fmt = fmt;
+    L->w = w; L->h = h;
+    L->cw = w >> fmt_hshift(fmt); L->ch = h >> fmt_vshift(fmt);  // what the encoder reads (mpegvideo_enc.c load_input_picture)
+    if (L->cw < 1 || L->ch < 1) return fail(e, H2J_ERR_UNSUPPORTED, "unsupported frame size %dx%d", w, h);
     L->y_pitch = w; L->c_pitch = fcw;
     L->u_off = (long long)w * h;
     L->v_off = L->u_off + (long long)fcw * fch;
     L->frame_stride = (long long)frame_stride;
-    L->mcu_w = (w + 15) >> 4; L->mcu_h = (h + 15) >> 4;
+    L->mb_w = (w + 15) >> 4;
+    L->mcu_w = (w + fmt_mcu_px_w(fmt) - 1) / fmt_mcu_px_w(fmt); L->mcu_h = (h + 15) >> 4;
     L->n_mcu = L->mcu_w * L->mcu_h;
-    L->n_blocks = L->n_mcu * 6;
+    L->n_blocks = L->n_mcu * fmt_mcu_blocks(fmt);
     auto al = [&](int a) {
         return ((uintptr_t)base % a) == 0 && (frame_stride % a) == 0 && (L->u_off % a) == 0 && (L->v_off % a) == 0 &&
                (L->y_pitch % a) == 0 && (L->c_pitch % a) == 0;
@@ -196,9 +204,9 @@ int make_layout(h2j_encoder *e, const uint8_t *base, size_t frame_stride, int w,
 // Rows that do not start on 8-byte boundaries would send every block of K1 / K2 down the bytewise path: such batches are
 // copied once to a 16-byte row pitch (repitch_kernel, ~1 us per 1080p frame) and the pipeline reads the copy.
 // On return sl.L describes what the pipeline reads and *pipe_src is where it reads it.
-size_t pitched_frame_bytes(int w, int h)
+size_t pitched_frame_bytes(int w, int h, int fmt)
 {
-    const int fcw = (w + 1) >> 1, fch = (h + 1) >> 1;
+    const int fcw = chroma_w(w, fmt), fch = chroma_h(h, fmt);
     return align_up(align_up((size_t)w, 16) * h + 2 * align_up((size_t)fcw, 16) * fch, 256);
 }
 
@@ -206,12 +214,12 @@ size_t pitched_frame_bytes(int w, int h)
 FrameLayout pitched_layout(const FrameLayout &T)
 {
     FrameLayout P = T;
-    const int fcw = (T.w + 1) >> 1, fch = (T.h + 1) >> 1;
+    const int fcw = chroma_w(T.w, T.fmt), fch = chroma_h(T.h, T.fmt);
     P.y_pitch = (int)align_up((size_t)T.w, 16);
     P.c_pitch = (int)align_up((size_t)fcw, 16);
     P.u_off = (long long)P.y_pitch * T.h;
     P.v_off = P.u_off + (long long)P.c_pitch * fch;
-    P.frame_stride = (long long)pitched_frame_bytes(T.w, T.h);
+    P.frame_stride = (long long)pitched_frame_bytes(T.w, T.h, T.fmt);
     P.aligned8 = 1;
     P.aligned16 = 1;
     return P;
@@ -225,7 +233,7 @@ int prepare_input(h2j_encoder *e, Slot &sl, const uint8_t *d_src, size_t src_str
     static const bool no_repitch = getenv("H2J_NO_REPITCH") != nullptr;  // measurement knob
     if (sl.L.aligned8 || no_repitch) return H2J_OK;
     if (!sl.d_pitched) {
-        const size_t bytes = pitched_frame_bytes(e->s.max_width, e->s.max_height) * (size_t)e->s.max_batch;
+        const size_t bytes = pitched_frame_bytes(e->s.max_width, e->s.max_height, e->s.chroma_format) * (size_t)e->s.max_batch;
         if (cudaMalloc(&sl.d_pitched, bytes) != cudaSuccess) {  // no room for the copy: the bytewise path still works
             cudaGetLastError();
             sl.d_pitched = nullptr;
@@ -234,9 +242,9 @@ int prepare_input(h2j_encoder *e, Slot &sl, const uint8_t *d_src, size_t src_str
     }
     const FrameLayout T = sl.L;
     const FrameLayout P = pitched_layout(T);
-    const int fch = (h + 1) >> 1;
-    const uint8_t *src_end = d_src + (size_t)(n - 1) * src_stride + tight_frame_bytes(w, h);
-    repitch_kernel<<<dim3((w + 128 * 16 - 1) / (128 * 16), (h + 2 * fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(d_src, T, sl.d_pitched, P, d_src, src_end);
+    const int fch = chroma_h(h, T.fmt);
+    const uint8_t *src_end = d_src + (size_t)(n - 1) * src_stride + tight_frame_bytes(w, h, T.fmt);
+    repitch_kernel<<<dim3((w + 128 * 16 - 1) / (128 * 16), (h + 2 * fch + kPlaneRowsPerCta - 1) / kPlaneRowsPerCta, n), 128, 0, sl.stream>>>(d_src, T, fch, sl.d_pitched, P, d_src, src_end);
     e->launches++;
     CU(e, cudaGetLastError());
     sl.L = P;
@@ -309,14 +317,16 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
         ScopedTiming t(e, sl, "fdct_quant_kernel");
         // consecutive tiles per CTA: as many as keep the grid at four waves or more (amortises the per-CTA set-up
         // and histogram flush), at most 16
-        int tiles_per_cta = (int)((long long)n_tiles * n * 3 / ((long long)e->sm_count * 16 * 4));
+        int tiles_per_cta = (int)((long long)n_tiles * n * fmt_roles(L.fmt) / ((long long)e->sm_count * 16 * 4));
         tiles_per_cta = tiles_per_cta < 1 ? 1 : (tiles_per_cta > e->fdct_tiles_per_cta ? e->fdct_tiles_per_cta : tiles_per_cta);
         if (const char *env = getenv("H2J_FDCT_TILES_PER_CTA")) tiles_per_cta = atoi(env) > 0 ? atoi(env) : tiles_per_cta;  // tuning knob
         if (e->force_fdct_tiles > 0) tiles_per_cta = e->force_fdct_tiles;
         // occupancy experiment knob: extra dynamic shared memory limits the CTAs resident per SM
         static const int extra_smem = getenv("H2J_K2_EXTRA_SMEM") ? atoi(getenv("H2J_K2_EXTRA_SMEM")) : 0;
-        const dim3 grid(3 * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
-        if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        const dim3 grid(fmt_roles(L.fmt) * ((n_tiles + tiles_per_cta - 1) / tiles_per_cta), n);
+        if (L.fmt == kFmt422) fdct_quant_fmt_kernel<kFmt422><<<grid, kFdctThreads, 0, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        else if (L.fmt == kFmt444) fdct_quant_fmt_kernel<kFmt444><<<grid, kFdctThreads, 0, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
+        else if (L.nv12) fdct_quant_kernel<true><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         else fdct_quant_kernel<false><<<grid, kFdctThreads, extra_smem, st>>>(d_frames, L, sl.d_state, sl.d_tabs, sl.d_images, e->images_cap, tiles_per_cta);
         e->launches++;
     }
@@ -326,11 +336,18 @@ int launch_pipeline(h2j_encoder *e, Slot &sl, const uint8_t *d_frames, int n, in
                                                                        e->d_comment, (int)e->comment.size());
         e->launches++;
     }
-    const int tiles_per_frame = (n_tiles + kEntFdctTiles - 1) / kEntFdctTiles;
     {
         ScopedTiming t(e, sl, "entropy_walk_kernel");
-        entropy_walk_kernel<<<dim3(tiles_per_frame, n), kEntThreads, kEntSmemBytes, st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info,
-                                                                                         e->units_cap, sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        const dim3 grid(n_tiles, n);
+        if (L.fmt == kFmt422)
+            entropy_walk_kernel<kFmt422><<<grid, fmt_tile_blocks(kFmt422), ent_smem_bytes(kFmt422), st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info, e->units_cap,
+                                                                                                     sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        else if (L.fmt == kFmt444)
+            entropy_walk_kernel<kFmt444><<<grid, fmt_tile_blocks(kFmt444), ent_smem_bytes(kFmt444), st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info, e->units_cap,
+                                                                                                     sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
+        else
+            entropy_walk_kernel<kFmt420><<<grid, fmt_tile_blocks(kFmt420), ent_smem_bytes(kFmt420), st>>>(L, sl.d_tabs, sl.d_images, e->images_cap, sl.d_unit_info, e->units_cap,
+                                                                                                     sl.d_stage_alloc, sl.d_stage, e->stage_cap_words);
         e->launches++;
     }
     {
@@ -483,6 +500,7 @@ void h2j_default_settings(h2j_settings *s)
     s->n_slots = 2;
     s->range_mode = H2J_RANGE_PASSTHROUGH;
     s->fixed_qscale = 0;
+    s->chroma_format = H2J_CHROMA_420;
     s->max_jpeg_bytes = 0;
     s->comment = nullptr;
     s->profile = 0;
@@ -543,6 +561,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     *out = nullptr;
     if (s->max_width < 2 || s->max_height < 2 || s->max_width > 65500 || s->max_height > 65500 || s->max_batch < 1 || s->n_slots < 1 ||
         s->n_slots > 8 || s->fixed_qscale < 0 || s->fixed_qscale > 31 || (s->range_mode != 0 && s->range_mode != 1) ||
+        s->chroma_format < H2J_CHROMA_420 || s->chroma_format > H2J_CHROMA_444 ||
         s->max_jpeg_bytes > ((size_t)256 << 20))  // bit positions inside a frame's scan are 32-bit
         return fail(nullptr, H2J_ERR_INVALID_ARG, "bad settings");
     int ndev = 0;
@@ -571,18 +590,20 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
 
     e->out_cap = align_up(s->max_jpeg_bytes ? s->max_jpeg_bytes : (size_t)2 * 1024 * 1024, 16);
     e->scan_cap_words = (long long)(e->out_cap / 4);
-    const int mcu_w = (s->max_width + 15) >> 4, mcu_h = (s->max_height + 15) >> 4;
+    const int fmt = s->chroma_format;
+    const int mcu_w = (s->max_width + fmt_mcu_px_w(fmt) - 1) / fmt_mcu_px_w(fmt), mcu_h = (s->max_height + 15) >> 4;
     const long long n_mcu = (long long)mcu_w * mcu_h;
-    e->images_cap = ((n_mcu + kTileMcus - 1) / kTileMcus + kEntFdctTiles - 1) / kEntFdctTiles * kEntFdctTiles;
-    e->blocks_cap = e->images_cap * kTileBlocks;
-    e->tiles_cap = (int)(e->images_cap / kEntFdctTiles);
-    e->units_cap = e->tiles_cap * kEntWarps;
+    e->images_cap = (n_mcu + kTileMcus - 1) / kTileMcus;
+    e->blocks_cap = e->images_cap * fmt_tile_blocks(fmt);
+    e->tiles_cap = (int)e->images_cap;
+    e->units_cap = e->tiles_cap * fmt_roles(fmt);  // units of 32 blocks: as many per tile as roles
     e->groups_cap = (e->units_cap + kPlaceGroupUnits - 1) / kPlaceGroupUnits;
     // a fixed place of one window per unit, then the reserved area for units that need more (every unit starts on a word:
     // at most one word of slack each)
     e->stage_cap_words = ((long long)e->units_cap * kWarpWinWords + e->scan_cap_words + e->units_cap + 3) / 4 * 4;  // (frames' areas stay 16-byte aligned)
     e->chunks_cap = (int)((e->scan_cap_words + kChunkWords - 1) >> kChunkShift);
-    e->frame_bytes_cap = std::max(align_up(tight_frame_bytes(s->max_width, s->max_height), 256), pitched_frame_bytes(s->max_width, s->max_height));
+    e->frame_bytes_cap = std::max(align_up(tight_frame_bytes(s->max_width, s->max_height, s->chroma_format), 256),
+                                  pitched_frame_bytes(s->max_width, s->max_height, s->chroma_format));
 
     // constant tables
     {
@@ -597,7 +618,9 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaMemcpy(e->d_comment, e->comment.c_str(), e->comment.size() + 1, cudaMemcpyHostToDevice));
     }
     if (getenv("H2J_K2_EXTRA_SMEM")) CUB(cudaFuncSetAttribute(fdct_quant_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUB(cudaFuncSetAttribute(entropy_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEntSmemBytes));
+    CUB(cudaFuncSetAttribute(entropy_walk_kernel<kFmt420>, cudaFuncAttributeMaxDynamicSharedMemorySize, ent_smem_bytes(kFmt420)));
+    CUB(cudaFuncSetAttribute(entropy_walk_kernel<kFmt422>, cudaFuncAttributeMaxDynamicSharedMemorySize, ent_smem_bytes(kFmt422)));
+    CUB(cudaFuncSetAttribute(entropy_walk_kernel<kFmt444>, cudaFuncAttributeMaxDynamicSharedMemorySize, ent_smem_bytes(kFmt444)));
 
     const int B = s->max_batch;
     e->slots.resize(s->n_slots);
@@ -606,7 +629,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
         CUB(cudaEventCreate(&sl.ev_begin));
         CUB(cudaEventCreate(&sl.ev_done));
         CUB(cudaMalloc(&sl.d_frames, e->frame_bytes_cap * B));
-        CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * kTileImageBytes));
+        CUB(cudaMalloc(&sl.d_images, (size_t)e->images_cap * B * fmt_tile_image_words(fmt) * 4));
         const size_t state_bytes = align_up(sizeof(FrameState) * B, 256);
         const size_t desc_bytes = align_up(sizeof(unsigned long long) * (size_t)e->groups_cap * B, 256);
         const size_t alloc_bytes = align_up(sizeof(unsigned int) * (size_t)B, 256);
@@ -633,7 +656,7 @@ int h2j_create(const h2j_settings *s, h2j_encoder **out)
     // single-frame staging (slot 0 only): planes in, JPEG / padded planes out
     {
         Slot &s0 = e->slots[0];
-        const size_t padded = (size_t)mcu_w * 16 * mcu_h * 16 * 3 / 2;
+        const size_t padded = (size_t)((s->max_width + 15) >> 4) * 16 * mcu_h * 16 * 3;
         s0.h_stage_bytes = std::max(std::max(e->frame_bytes_cap, e->out_cap), padded);
         CUB(cudaHostAlloc(&s0.h_stage, s0.h_stage_bytes, cudaHostAllocDefault));
         CUB(cudaHostAlloc(&s0.h_tail, 64, cudaHostAllocDefault));
@@ -650,7 +673,7 @@ int h2j_submit_device(h2j_encoder *e, int slot, const uint8_t *d_frames, size_t 
     Slot &sl = e->slots[slot];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
     if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
-    if (frame_stride < tight_frame_bytes(width, height)) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
+    if (frame_stride < tight_frame_bytes(width, height, e->s.chroma_format)) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
     ON_DEVICE(e);
     sl.n = n;
     CU(e, cudaEventRecord(sl.ev_begin, sl.stream));
@@ -672,11 +695,12 @@ int h2j_submit_device_nv12(h2j_encoder *e, int slot, const uint8_t *d_frames, si
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
     if (!d_frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
     if (width < 2 || height < 2) return fail(e, H2J_ERR_UNSUPPORTED, "unsupported frame size %dx%d", width, height);
+    if (e->s.chroma_format != H2J_CHROMA_420) return fail(e, H2J_ERR_UNSUPPORTED, "NV12 is a 4:2:0 layout; this encoder was created for another chroma format");
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
     if (pitch < width || pitch < 2 * fcw) return fail(e, H2J_ERR_INVALID_ARG, "pitch %d smaller than a row of %d samples", pitch, width);
     if (uv_offset < (size_t)pitch * height || frame_stride < uv_offset + (size_t)pitch * (fch - 1) + 2 * (size_t)fcw)
         return fail(e, H2J_ERR_INVALID_ARG, "uv_offset / frame_stride do not hold an NV12 frame of %dx%d at pitch %d", width, height, pitch);
-    const size_t fb = tight_frame_bytes(width, height);
+    const size_t fb = tight_frame_bytes(width, height, e->s.chroma_format);
     const size_t dstride = align_up(fb, 256);
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
     ON_DEVICE(e);
@@ -725,7 +749,7 @@ int h2j_submit_host(h2j_encoder *e, int slot, const uint8_t *frames, size_t fram
     Slot &sl = e->slots[slot];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot %d has a batch in flight", slot);
     if (!frames || n < 1 || n > e->s.max_batch) return fail(e, H2J_ERR_INVALID_ARG, "bad frames pointer or batch size %d (max %d)", n, e->s.max_batch);
-    const size_t fb = tight_frame_bytes(width, height);
+    const size_t fb = tight_frame_bytes(width, height, e->s.chroma_format);
     if (frame_stride < fb) return fail(e, H2J_ERR_INVALID_ARG, "frame_stride smaller than one frame");
     ON_DEVICE(e);
     // device copy keeps frames at a 256-byte aligned stride so the vector-load paths apply
@@ -844,12 +868,12 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
         return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d outside 2x2 .. %dx%d", width, height, e->s.max_width, e->s.max_height);
     Slot &sl = e->slots[0];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
-    const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
+    const int fcw = chroma_w(width, e->s.chroma_format), fch = chroma_h(height, e->s.chroma_format);
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
     // AVFrame planes -> tight I420 in pinned memory (the only host-side touch of the pixels): copied in pieces, every
     // piece uploaded as soon as it is in place, so that the DMA of one piece runs under the memcpy of the next
     ON_DEVICE(e);
-    const size_t fb = tight_frame_bytes(width, height);
+    const size_t fb = tight_frame_bytes(width, height, e->s.chroma_format);
     const size_t dstride = align_up(fb, 256);
     if (dstride > e->frame_bytes_cap) return fail(e, H2J_ERR_UNSUPPORTED, "frame %dx%d exceeds the configured maximum", width, height);
     int rc = make_layout(e, sl.d_frames, dstride, width, height, &sl.L);
@@ -928,6 +952,7 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
     if (range_mode != H2J_RANGE_PASSTHROUGH && range_mode != H2J_RANGE_LIMITED_TO_FULL) return fail(e, H2J_ERR_INVALID_ARG, "bad range_mode %d", range_mode);
     Slot &sl = e->slots[0];
     if (sl.busy) return fail(e, H2J_ERR_BUSY, "slot 0 has a batch in flight");
+    if (e->s.chroma_format != H2J_CHROMA_420) return fail(e, H2J_ERR_UNSUPPORTED, "h2j_convert_pad handles 4:2:0 frames (the reference's format) only");
     const int fcw = (width + 1) >> 1, fch = (height + 1) >> 1;
     if (strides[0] < width || strides[1] < fcw || strides[2] < fcw) return fail(e, H2J_ERR_INVALID_ARG, "stride smaller than the row");
     ON_DEVICE(e);
@@ -938,7 +963,7 @@ int h2j_convert_pad(h2j_encoder *e, const uint8_t *const planes[3], const int st
         for (int r = 0; r < fch; r++) memcpy(p + (size_t)r * fcw, planes[pl] + (size_t)r * strides[pl], fcw);
         p += (size_t)fcw * fch;
     }
-    const size_t fb = tight_frame_bytes(width, height);
+    const size_t fb = tight_frame_bytes(width, height, e->s.chroma_format);
     FrameLayout L;
     int rc = make_layout(e, sl.d_frames, align_up(fb, 256), width, height, &L);
     if (rc) return rc;
@@ -998,14 +1023,16 @@ int h2j_debug_coefficients(h2j_encoder *e, int slot, int frame, int16_t *out, si
     CU(e, cudaStreamSynchronize(sl.stream));
     // tile images -> dense blocks; halfword 0 of a record is the DC difference, so the levels are rebuilt by
     // running the encoder's predictors (one per component, reset to 128) over the blocks in coding order
+    const int fmt = sl.L.fmt, tile_blocks = fmt_tile_blocks(fmt), tile_words = fmt_tile_image_words(fmt);
     const int n_tiles = (sl.L.n_mcu + kTileMcus - 1) / kTileMcus;
-    std::vector<int16_t> img((size_t)n_tiles * kTileImageWords * 2);
-    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->images_cap * kTileImageWords, img.size() * sizeof(int16_t),
+    std::vector<int16_t> img((size_t)n_tiles * tile_words * 2);
+    CU(e, cudaMemcpy(img.data(), sl.d_images + (size_t)frame * e->images_cap * tile_words, img.size() * sizeof(int16_t),
                      cudaMemcpyDeviceToHost));
     int last_dc[3] = {128, 128, 128};
     for (int b = 0; b < sl.L.n_blocks; b++) {
-        const int16_t *rec = img.data() + ((size_t)(b / kTileBlocks) * kTileImageWords + (size_t)tile_rec_word(b % kTileBlocks)) * 2;
-        const int n = b % 6, comp = n < 4 ? 0 : n - 3;
+        const TileRec tr = tile_rec_fmt(fmt, b % tile_blocks);
+        const int16_t *rec = img.data() + ((size_t)(b / tile_blocks) * tile_words + (size_t)tr.sub * kSubImageWords + (size_t)tr.idx * kBlkWords) * 2;
+        const int comp = block_component(fmt, b % fmt_mcu_blocks(fmt));
         last_dc[comp] += rec[0];
         out[(size_t)b * 64] = (int16_t)last_dc[comp];
         for (int k = 1; k < 64; k++) out[(size_t)b * 64 + k] = rec[2 * (k & 31) + (k >> 5)];

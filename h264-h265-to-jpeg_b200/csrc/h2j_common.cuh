@@ -32,7 +32,26 @@ struct FrameLayout {
     int range_mode;
     int fixed_qscale;
     int nv12;          // chroma is ONE plane of interleaved Cb/Cr pairs at u_off, rows c_pitch apart (v_off unused)
+    int fmt;           // kFmt420 (what the reference opens its encoder as), kFmt422, kFmt444: MCU geometry, see below
+    int mb_w;          // 16x16 luma macroblocks per row (= mcu_w except at 4:4:4, whose MCUs are 8 wide): what K1 walks
 };
+
+// ---- chroma formats ------------------------------------------------------------------------------
+// libavcodec's mjpeg encoder codes (mjpegenc.c ff_mjpeg_encode_mb, mjpegenc_common.c ff_mjpeg_init_hvsample)
+//   4:2:0  16x16 MCUs of Y0 Y1 Y2 Y3 Cb Cr               (6 blocks; Y 2x2, chroma 1x1)      -- the reference's format
+//   4:2:2  16x16 MCUs of Y0 Y1 Y2 Y3 Cb0 Cb1 Cr0 Cr1     (8 blocks; Y 2x2, chroma 1x2: top, bottom)
+//   4:4:4   8x16 MCUs of Y0 Y1 Cb0 Cb1 Cr0 Cr1           (6 blocks; every component 1x2: top, bottom)
+// A K2 tile is 16 consecutive MCUs whatever the format; its blocks are dealt to single-warp ROLES of 32 blocks each:
+//   4:2:0  3 roles: luma of MCUs 0-7 (record = mcu * 4 + n), luma of MCUs 8-15, Cb (records 0-15) + Cr (16-31)
+//   4:2:2  4 roles: luma of MCUs 0-7, luma of MCUs 8-15, Cb of the 16 MCUs (record = mcu * 2 + n), Cr
+//   4:4:4  3 roles: Y of the 16 MCUs (record = mcu * 2 + n), Cb, Cr
+enum { kFmt420 = 0, kFmt422 = 1, kFmt444 = 2 };
+__host__ __device__ constexpr int fmt_roles(int fmt) { return fmt == kFmt422 ? 4 : 3; }
+__host__ __device__ constexpr int fmt_mcu_blocks(int fmt) { return fmt == kFmt422 ? 8 : 6; }
+__host__ __device__ constexpr int fmt_tile_blocks(int fmt) { return 16 * fmt_mcu_blocks(fmt); }  // 96 / 128 / 96 = roles * 32
+__host__ __device__ constexpr int fmt_hshift(int fmt) { return fmt == kFmt444 ? 0 : 1; }        // chroma subsampling
+__host__ __device__ constexpr int fmt_vshift(int fmt) { return fmt == kFmt420 ? 1 : 0; }
+__host__ __device__ constexpr int fmt_mcu_px_w(int fmt) { return fmt == kFmt444 ? 8 : 16; }      // MCU width in luma samples
 
 // ---- coefficient store ("tile images") -----------------------------------------------------------
 // K2 works on tiles of 16 consecutive MCUs (96 blocks).  A tile leaves K2 as one contiguous image made of three
@@ -72,14 +91,32 @@ __host__ __device__ inline TileRec tile_rec(int b)
 }
 __host__ __device__ inline int tile_rec_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + r.idx * kBlkWords; }
 __host__ __device__ inline int tile_maskhi_word(int b) { const TileRec r = tile_rec(b); return r.sub * kSubImageWords + kSubMaskHiOff + r.idx; }
+// the same for any format: block b of a tile in coding order -> (role's sub-image, record), and the block's component
+__host__ __device__ inline TileRec tile_rec_fmt(int fmt, int b)
+{
+    if (fmt == kFmt420) return tile_rec(b);
+    TileRec r;
+    if (fmt == kFmt444) {
+        const int m = b / 6, n = b - 6 * m;  // Y0 Y1 Cb0 Cb1 Cr0 Cr1
+        r.sub = n >> 1;
+        r.idx = m * 2 + (n & 1);
+    } else {
+        const int m = b >> 3, n = b & 7;     // Y0 Y1 Y2 Y3 Cb0 Cb1 Cr0 Cr1
+        if (n < 4) { r.sub = m >> 3; r.idx = (m & 7) * 4 + n; }
+        else { r.sub = 2 + ((n - 4) >> 1); r.idx = m * 2 + (n & 1); }
+    }
+    return r;
+}
+__host__ __device__ inline int block_component(int fmt, int n)  // n = position of the block in its MCU (coding order)
+{
+    if (fmt == kFmt420) return n < 4 ? 0 : n - 3;
+    if (fmt == kFmt444) return n >> 1;
+    return n < 4 ? 0 : 1 + ((n - 4) >> 1);
+}
+__host__ __device__ inline int fmt_tile_image_words(int fmt) { return fmt_roles(fmt) * kSubImageWords; }
 constexpr int kFdctThreads = 32;                           // K2: single-warp CTAs, three roles per tile
 
-#ifndef H2J_ENT_FDCT_TILES
-#define H2J_ENT_FDCT_TILES 1
-#endif
-constexpr int kEntFdctTiles = H2J_ENT_FDCT_TILES;            // K2 tiles per K4a CTA: 1 (0.749 ms at 512 x 1080p) against 2 (0.775 ms)
-constexpr int kEntBlocks = kEntFdctTiles * kTileBlocks;     // 192
-constexpr int kEntThreads = kEntBlocks;
+constexpr int kEntThreads = kTileBlocks;                    // K4a: one CTA per K2 tile (two per CTA measured 3 % slower), a thread per block
 constexpr int kMaxBitsPerBlock = 27 * 64;                   // DC (16+11) + 63 * (16+11); ZRLs only replace coefficients
 
 constexpr int kHuffGroup = 128;                             // threads per table

@@ -1,9 +1,10 @@
 // K4: entropy coding (mjpegenc.c record_block + ff_mjpeg_encode_picture_frame), in two kernels.
 //
 // K4a entropy_walk_kernel -- all the coding work, no dependency between CTAs or warps:
-//   A CTA takes kEntFdctTiles K2 tiles of one frame (one: 96 consecutive blocks) and pulls the tile image (levels
-//   and non-zero masks) and the frame's code tables into shared memory with bulk copies (cp.async.bulk -> SASS
-//   UBLKCP) signalled on an mbarrier.  Each of the CTA's warps then works alone on its UNIT of 32 blocks:
+//   A CTA takes one K2 tile of one frame (16 MCUs: 96 consecutive blocks at 4:2:0 and 4:4:4, 128 at 4:2:2) and pulls the
+//   tile image (levels and non-zero masks) and the frame's code tables into shared memory with bulk copies
+//   (cp.async.bulk -> SASS UBLKCP) signalled on an mbarrier.  Each of the CTA's warps then works alone on its UNIT of 32
+//   blocks in coding order (a thread finds its block's record through tile_rec_fmt):
 //     1. ONE walk over the block: every lane encodes its block into a private 256-bit slot in shared memory and
 //        learns its bit length on the way (a block that needs more keeps counting and is emitted directly in 2);
 //        warp scan of the lengths.
@@ -49,7 +50,7 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 constexpr int kWalkPerTrip = H2J_ENT_WALK;                   // K4a: non-zero levels a lane takes per trip of its walk (per 2048
                                                              // frames: 1 -> 2.927 ms, 2 -> 2.758, 3 -> 2.834, 4 -> 2.907)
 constexpr int kUnitBlocks = 32;                              // one warp
-constexpr int kEntWarps = kEntThreads / 32;                  // units per CTA
+constexpr int kEntWarps = kEntThreads / 32;                  // units per CTA at 4:2:0 / 4:4:4 (4:2:2: four)
 constexpr int kWarpWinWords = 256;                           // per-warp bit window: 8 Kibit
 constexpr int kWarpWinBits = kWarpWinWords * 32;
 constexpr int kWarpWinStride = kWarpWinWords + 4;            // spare words for the last partial OR
@@ -207,32 +208,40 @@ __device__ __forceinline__ unsigned walk_block(const int16_t *cb, unsigned mask_
 }
 
 constexpr int kEntTabBytes = (2 * 16 + 2 * 256) * 4;  // DC luma/chroma (16 entries each), AC luma/chroma of FrameTab::hcode
-constexpr int kEntSmemBytes = kEntFdctTiles * kTileImageBytes + kEntTabBytes + kEntWarps * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
+// dynamic shared memory of a CTA: the tile image, the code tables, a window and 32 slots per warp
+__host__ __device__ constexpr int ent_smem_bytes(int fmt)
+{
+    return fmt_roles(fmt) * kSubImageBytes + kEntTabBytes + fmt_roles(fmt) * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
+}
+constexpr int kEntSmemBytes = ent_smem_bytes(kFmt420);
 static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0, "hcode must be bulk-copyable");
 
-// grid (tiles_per_frame, frames)
-__global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L, FrameTab *__restrict__ tabs,
+// grid (tiles_per_frame, frames); FMT = the chroma format (h2j_common.cuh): a tile is 96 blocks (three units) at 4:2:0 and
+// 4:4:4, 128 blocks (four units) at 4:2:2; one thread per block, one warp per unit
+template <int FMT>
+__global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(FrameLayout L, FrameTab *__restrict__ tabs,
                                                                    const uint32_t *__restrict__ images, long long images_cap,
                                                                    unsigned long long *__restrict__ unit_info, int units_cap,
                                                                    unsigned int *__restrict__ stage_alloc,  // [frame] words handed out
                                                                    uint32_t *__restrict__ stage, long long stage_cap_words)
 {
+    constexpr int kWarps = fmt_roles(FMT), kThreads = fmt_tile_blocks(FMT);       // units per tile = roles per tile
+    constexpr int kImageWords = kWarps * kSubImageWords, kImageBytes = kImageWords * 4;
     extern __shared__ __align__(128) unsigned char ent_smem[];
-    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                                    // the CTA's tile images
-    uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kEntFdctTiles * kTileImageBytes);  // [2][16] DC code tables
-    uint32_t *s_hac = s_hdc + 32;                                                                // [2][256] AC code tables
-    unsigned int *s_win_all = s_hac + 512;                                                       // [warp][kWarpWinStride]
-    unsigned int *s_slot_all = s_win_all + kEntWarps * kWarpWinStride;                           // [warp][lane][kSlotStride]
+    uint32_t *s_img = reinterpret_cast<uint32_t *>(ent_smem);                    // the CTA's tile image
+    uint32_t *s_hdc = reinterpret_cast<uint32_t *>(ent_smem + kImageBytes);      // [2][16] DC code tables
+    uint32_t *s_hac = s_hdc + 32;                                                // [2][256] AC code tables
+    unsigned int *s_win_all = s_hac + 512;                                       // [warp][kWarpWinStride]
+    unsigned int *s_slot_all = s_win_all + kWarps * kWarpWinStride;              // [warp][lane][kSlotStride]
     __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.y, tile = blockIdx.x;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
-        // images_cap is even, so both images of the tile exist in the buffer even when the second holds no block
-        const uint32_t *src = images + ((long long)f * images_cap + (long long)tile * kEntFdctTiles) * kTileImageWords;
-        mbar_expect_tx(&s_bar, kEntFdctTiles * kTileImageBytes + kEntTabBytes);
-        bulk_g2s(s_img, src, kEntFdctTiles * kTileImageBytes, &s_bar);
+        const uint32_t *src = images + ((long long)f * images_cap + tile) * kImageWords;
+        mbar_expect_tx(&s_bar, kImageBytes + kEntTabBytes);
+        bulk_g2s(s_img, src, kImageBytes, &s_bar);
         bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
         bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
@@ -243,22 +252,23 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
         const long long lin = (long long)f * gridDim.x + tile + kEntPrefetchDistance;
         if (lin < (long long)gridDim.x * gridDim.y) {
             const long long f2 = lin / gridDim.x, t2 = lin - f2 * gridDim.x;
-            bulk_prefetch_l2(images + (f2 * images_cap + t2 * kEntFdctTiles) * kTileImageWords, kEntFdctTiles * kTileImageBytes);
+            bulk_prefetch_l2(images + (f2 * images_cap + t2) * kImageWords, kImageBytes);
         }
     }
-    static_assert((kEntWarps * kWarpWinStride) % 4 == 0 && (kEntFdctTiles * kTileImageBytes + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
-    for (int i = tid; i < kEntWarps * kWarpWinStride / 4; i += kEntThreads) reinterpret_cast<uint4 *>(s_win_all)[i] = make_uint4(0, 0, 0, 0);  // while the copies are on their way
+    static_assert((kWarps * kWarpWinStride) % 4 == 0 && (kImageBytes + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
+    for (int i = tid; i < kWarps * kWarpWinStride / 4; i += kThreads) reinterpret_cast<uint4 *>(s_win_all)[i] = make_uint4(0, 0, 0, 0);  // while the copies are on their way
     __syncthreads();  // barrier initialised, windows cleared (clearing only the words a unit needs, once its length is
                       // known, executes fewer instructions but measured 1 % slower: here it hides under the copy)
 
     // ---- from here on the warp is on its own ----
-    const int u = tile * kEntWarps + warp;                  // unit index inside the frame
-    const int b = u * kUnitBlocks + lane;                   // == tile * kEntBlocks + tid
+    const int u = tile * kWarps + warp;                     // unit index inside the frame
+    const int b = u * kUnitBlocks + lane;                   // == tile * kThreads + tid
     if (u * kUnitBlocks >= L.n_blocks) return;              // trailing unit of the frame's last tile: no block at all
     const bool valid = b < L.n_blocks;
-    const int img_i = tid >= kTileBlocks ? 1 : 0, blk_i = tid - img_i * kTileBlocks;  // K2 image, block inside it (coding order)
-    const uint32_t *rec = s_img + img_i * kTileImageWords + tile_rec_word(blk_i);
-    const int cls = (tid % 6) < 4 ? 0 : 1;  // 192 is a multiple of 6: the block's position in its MCU is tid % 6
+    const TileRec tr = tile_rec_fmt(FMT, tid);              // block of the tile (coding order) -> (role's sub-image, record)
+    const uint32_t *rec = s_img + tr.sub * kSubImageWords + tr.idx * kBlkWords;
+    // the tile starts on an MCU boundary, so the block's position in its MCU is tid % blocks per MCU
+    const int cls = block_component(FMT, tid % fmt_mcu_blocks(FMT)) ? 1 : 0;
     const int16_t *cb = reinterpret_cast<const int16_t *>(rec);
     const uint32_t *hdc = s_hdc + 16 * cls, *hac = s_hac + 256 * cls;
     unsigned int *win = s_win_all + warp * kWarpWinStride;
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(kEntThreads) entropy_walk_kernel(FrameLayout L
     unsigned mask_lo = 0, mask_hi = 0;
     if (valid) {
         mask_lo = rec[kMaskLoWord];
-        mask_hi = s_img[img_i * kTileImageWords + tile_maskhi_word(blk_i)];
+        mask_hi = s_img[tr.sub * kSubImageWords + kSubMaskHiOff + tr.idx];
     }
 
     // ---- 1. the walk: bits into the private slot, length on the way ----

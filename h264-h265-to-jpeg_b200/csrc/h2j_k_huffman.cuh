@@ -380,8 +380,11 @@ __device__ uint8_t header_byte(int i, const HeaderPlan &h, const FrameTab *T, co
         return T->vals[t][j - 17];
     }
     const int k = i - h.off_sof;
+    // sampling factors (mjpegenc_common.c ff_mjpeg_init_hvsample): luma 2x2 and chroma 2 >> shift, but 4:4:4 is coded with
+    // every component at h = 1, v = 2 (8x16 MCUs)
+    const uint8_t hv_y = L.fmt == kFmt444 ? 0x12 : 0x22, hv_c = L.fmt == kFmt420 ? 0x11 : 0x12;
     const uint8_t tail[33] = {0xff, 0xc0, 0, 17, 8, (uint8_t)(L.h >> 8), (uint8_t)L.h, (uint8_t)(L.w >> 8), (uint8_t)L.w, 3,
-                              1, 0x22, 0, 2, 0x11, 0, 3, 0x11, 0,
+                              1, hv_y, 0, 2, hv_c, 0, 3, hv_c, 0,
                               0xff, 0xda, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
     return tail[k];
 }

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) mbvar_kernel(const uint8_t *__restrict__ 
     const int f = blockIdx.y, my = blockIdx.x;
     const uint8_t *Y = frames + (long long)f * L.frame_stride;
     int local = 0;
-    for (int mx = threadIdx.x; mx < L.mcu_w; mx += blockDim.x) {
+    for (int mx = threadIdx.x; mx < L.mb_w; mx += blockDim.x) {  // 16x16 macroblocks (= MCUs except at 4:4:4)
         unsigned sum = 0, norm = 0;
         const int x0 = mx * 16;
         if (L.aligned16 && x0 + 16 <= L.w && L.range_mode == 0) {
@@ -187,11 +187,11 @@ __global__ void __launch_bounds__(128) nv12_to_i420_kernel(const uint8_t *__rest
 // the pipeline (edges are replicated from the last real sample).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) repitch_kernel(const uint8_t *__restrict__ src, FrameLayout T,  // tight layout of the source
+                                                      int fch,                                         // rows of a chroma plane
                                                       uint8_t *__restrict__ dst, FrameLayout P,        // pitched layout of the copy
                                                       const uint8_t *src_begin, const uint8_t *src_end)
 {
     const int f = blockIdx.z;
-    const int fch = (T.h + 1) >> 1;
     for (int row = blockIdx.y * kPlaneRowsPerCta; row < min((int)(blockIdx.y + 1) * kPlaneRowsPerCta, T.h + 2 * fch); row++) {
     int pw, r;
     long long so, dof;

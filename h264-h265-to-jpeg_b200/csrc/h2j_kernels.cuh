@@ -3,6 +3,7 @@
 #include "h2j_common.cuh"
 #include "h2j_k_planes.cuh"
 #include "h2j_k_fdct.cuh"
+#include "h2j_k_fdct_fmt.cuh"
 #include "h2j_k_huffman.cuh"
 #include "h2j_k_entropy.cuh"
 #include "h2j_k_stuff.cuh"

@@ -32,6 +32,17 @@ ERR_BUFFER_TOO_SMALL = -7
 RANGE_PASSTHROUGH = 0
 RANGE_LIMITED_TO_FULL = 1
 
+CHROMA_420 = 0  # what the reference opens its encoder as (src/Encoder.cpp:162)
+CHROMA_422 = 1
+CHROMA_444 = 2
+
+
+def chroma_shape(width: int, height: int, chroma_format: int = CHROMA_420) -> Tuple[int, int]:
+    """(rows, columns) of a chroma plane of a width x height frame"""
+    hs = 0 if chroma_format == CHROMA_444 else 1
+    vs = 1 if chroma_format == CHROMA_420 else 0
+    return (height + (1 << vs) - 1) >> vs, (width + (1 << hs) - 1) >> hs
+
 
 class H2JError(RuntimeError):
     def __init__(self, status: int, message: str):
@@ -51,6 +62,7 @@ class Settings(C.Structure):
         ("max_jpeg_bytes", C.c_size_t),
         ("comment", C.c_char_p),
         ("profile", C.c_int),
+        ("chroma_format", C.c_int),
     ]
 
 
@@ -132,13 +144,14 @@ def load_library() -> C.CDLL:
     return lib
 
 
-def frame_bytes(width: int, height: int) -> int:
-    """Bytes of one tightly packed I420 frame (Y, U, V with ceil-halved chroma)."""
-    return width * height + 2 * ((width + 1) // 2) * ((height + 1) // 2)
+def frame_bytes(width: int, height: int, chroma_format: int = CHROMA_420) -> int:
+    """Bytes of one tightly packed planar frame (Y, U, V; I420 by default)."""
+    ch, cw = chroma_shape(width, height, chroma_format)
+    return width * height + 2 * cw * ch
 
 
-def split_planes(frame: np.ndarray, width: int, height: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    cw, ch = (width + 1) // 2, (height + 1) // 2
+def split_planes(frame: np.ndarray, width: int, height: int, chroma_format: int = CHROMA_420) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    ch, cw = chroma_shape(width, height, chroma_format)
     y = frame[: width * height].reshape(height, width)
     u = frame[width * height: width * height + cw * ch].reshape(ch, cw)
     v = frame[width * height + cw * ch: width * height + 2 * cw * ch].reshape(ch, cw)
@@ -232,7 +245,7 @@ class Encoder:
 
     def __init__(self, max_width: int = 1920, max_height: int = 1088, max_batch: int = 16, n_slots: int = 2, device: int = 0,
                  range_mode: int = RANGE_PASSTHROUGH, fixed_qscale: int = 0, max_jpeg_bytes: int = 0,
-                 comment: Optional[bytes] = None, profile: bool = False):
+                 comment: Optional[bytes] = None, profile: bool = False, chroma_format: int = CHROMA_420):
         self._lib = load_library()
         s = Settings()
         self._lib.h2j_default_settings(C.byref(s))
@@ -240,6 +253,8 @@ class Encoder:
         s.range_mode, s.fixed_qscale, s.max_jpeg_bytes = range_mode, fixed_qscale, max_jpeg_bytes
         s.comment = comment
         s.profile = 1 if profile else 0
+        s.chroma_format = chroma_format
+        self.chroma_format = chroma_format
         self._h = C.c_void_p()
         rc = self._lib.h2j_create(C.byref(s), C.byref(self._h))
         if rc != OK:
@@ -270,11 +285,10 @@ class Encoder:
         if rc < 0:
             raise H2JError(rc, (self._lib.h2j_last_error(self._h) or b"").decode())
 
-    @staticmethod
-    def _check_chroma(w: int, h: int, u: np.ndarray, v: np.ndarray) -> None:
-        want = ((h + 1) // 2, (w + 1) // 2)
+    def _check_chroma(self, w: int, h: int, u: np.ndarray, v: np.ndarray) -> None:
+        want = chroma_shape(w, h, self.chroma_format)
         if u.shape != want or v.shape != want:
-            raise H2JError(ERR_INVALID_ARG, f"chroma planes must be {want[0]}x{want[1]} (ceil-halved luma), got {u.shape} / {v.shape}")
+            raise H2JError(ERR_INVALID_ARG, f"chroma planes must be {want[0]}x{want[1]} for this encoder's chroma format, got {u.shape} / {v.shape}")
 
     # -- single frame, the Encoder::yuv2Jpeg shape --------------------------------------------
     def yuv2jpeg(self, y: np.ndarray, u: np.ndarray, v: np.ndarray) -> bytes:

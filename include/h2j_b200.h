@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define H2J_ABI_VERSION 2
+#define H2J_ABI_VERSION 3
 
 typedef enum h2j_status {
     H2J_OK = 0,
@@ -56,6 +56,16 @@ typedef enum h2j_range_mode {
     H2J_RANGE_LIMITED_TO_FULL = 1
 } h2j_range_mode;
 
+/* Chroma format of the frames an encoder takes.  The reference opens libavcodec's mjpeg encoder as yuvj420p and nothing
+ * else (src/Encoder.cpp:162): H2J_CHROMA_420 is the drop-in.  The other two are the same encoder at its other MCU
+ * geometries (yuvj422p: 16x16 MCUs of 4 Y + 2 Cb + 2 Cr blocks; yuvj444p: 8x16 MCUs of 2 Y + 2 Cb + 2 Cr), byte-identical
+ * to what that libavcodec writes for planar 4:2:2 / 4:4:4 frames. */
+typedef enum h2j_chroma_format {
+    H2J_CHROMA_420 = 0, /* planes: Y w x h, U and V ceil(w/2) x ceil(h/2) */
+    H2J_CHROMA_422 = 1, /* U and V ceil(w/2) x h */
+    H2J_CHROMA_444 = 2  /* U and V w x h */
+} h2j_chroma_format;
+
 typedef struct h2j_settings {
     int device;            /* CUDA device ordinal */
     int max_width;         /* largest frame the encoder will be asked for */
@@ -69,6 +79,7 @@ typedef struct h2j_settings {
     const char *comment;   /* COM segment payload; NULL = "Lavc58.117.101", the LIBAVCODEC_IDENT of the
                               ffmpeg build the reference links on x86-64 (lib/ffmpeg/x86_64_shared) */
     int profile;           /* non-zero: bracket every kernel with CUDA events (see h2j_slot_kernel_ms) */
+    int chroma_format;     /* h2j_chroma_format of every frame this encoder is given (default H2J_CHROMA_420) */
 } h2j_settings;
 
 typedef struct h2j_encoder h2j_encoder;
@@ -87,15 +98,16 @@ int h2j_device_count(void);
 /*
  * One frame, host planes in, JPEG bytes out, synchronous — the drop-in for
  * Encoder::yuv2Jpeg() (reference src/Encoder.cpp:104).  planes/strides follow AVFrame.data/.linesize for
- * an 8-bit 4:2:0 planar frame: plane 0 is width x height, planes 1/2 are ceil(width/2) x ceil(height/2).
+ * an 8-bit 4:2:0 planar frame: plane 0 is width x height, planes 1/2 are ceil(width/2) x ceil(height/2) (for an encoder
+ * created with another chroma_format: ceil(width/2) x height at 4:2:2, width x height at 4:4:4).
  * Uses slot 0; the planes are staged through pinned memory and copied asynchronously.
  */
 int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height,
                      uint8_t *out, size_t out_capacity, size_t *out_size);
 
 /*
- * Batches.  Frames are same-sized, tightly packed I420: Y (w*h), U (cw*ch), V (cw*ch) with
- * cw = ceil(w/2), ch = ceil(h/2); consecutive frames are frame_stride bytes apart.
+ * Batches.  Frames are same-sized, tightly packed planar: Y (w*h), U (cw*ch), V (cw*ch) with cw = ceil(w/2), ch = ceil(h/2)
+ * for 4:2:0 (I420; cw x h for 4:2:2, w x h for 4:4:4: settings.chroma_format); consecutive frames are frame_stride bytes apart.
  *
  * h2j_submit_host:   frames live in HOST memory (pinned for full PCIe speed); the copy to the device, the
  *                    kernels and nothing else are enqueued on the slot's stream.  Returns immediately.

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/h2j_b200.h but not exported"
     assert set(h2j_b200.EXPORTS) <= set(names)
-    assert lib.h2j_abi_version() == 2
+    assert lib.h2j_abi_version() == 3
 
 
 def test_status_strings_and_defaults():
@@ -33,7 +33,15 @@ def test_status_strings_and_defaults():
     lib = h2j_b200.load_library()
     s = h2j_b200.Settings()
     lib.h2j_default_settings(C.byref(s))
-    assert (s.max_width, s.max_height, s.range_mode, s.fixed_qscale) == (1920, 1088, 0, 0)
+    assert (s.max_width, s.max_height, s.range_mode, s.fixed_qscale, s.chroma_format) == (1920, 1088, 0, 0, 0)
+    import ctypes
+
+    # the binding's struct is the header's struct (a field appended in C without the Python side following would shift nothing
+    # visible here but truncate the copy in h2j_create)
+    hdr = open(os.path.join(ROOT, "include", "h2j_b200.h")).read()
+    body = hdr[hdr.index("typedef struct h2j_settings {"): hdr.index("} h2j_settings;")]
+    fields = re.findall(r"^\s+(?:const\s+)?(?:int|size_t|char)\s*\*?\s*(\w+);", body, flags=re.M)
+    assert fields == [f[0] for f in h2j_b200.Settings._fields_], fields
     assert lib.h2j_status_string(0) == b"ok"
     assert b"CUDA" in lib.h2j_status_string(-2)
 
