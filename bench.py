@@ -68,10 +68,12 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------------
 # synthetic workload: textured frames (smooth gradients + band-limited texture + mild noise), made on the GPU
 # ------------------------------------------------------------------------------------------------------
-def make_frames_torch(n, w, h, device, seed0=0):
+def make_frames_torch(n, w, h, device, seed0=0, chroma_format=0):
     import torch
 
-    cw, ch = (w + 1) // 2, (h + 1) // 2
+    import h2j_b200
+
+    ch, cw = h2j_b200.chroma_shape(w, h, chroma_format)
     fb = w * h + 2 * cw * ch
     stride = (fb + 255) // 256 * 256
     out = torch.zeros((n, stride), dtype=torch.uint8, device=device)
@@ -387,13 +389,13 @@ def device_plan(torch, local_rank, world):
     return plan["gpus"][local_rank], f"rank i on GPU {plan['gpus']}[i] -- {plan['how']}", plan["rates"]
 
 
-def oracle_jpeg(frame_bytes, w, h):
-    """JPEG the oracle (CPU restatement of the reference's encoder) makes of one tight I420 frame."""
+def oracle_jpeg(frame_bytes, w, h, chroma_format=0):
+    """JPEG the oracle (CPU restatement of the reference's encoder) makes of one tight planar frame."""
     import h2j_b200
     from tests.support import oracle as orc
 
-    y, u, v = h2j_b200.split_planes(frame_bytes, w, h)
-    return orc.oracle_encode(np.ascontiguousarray(y), np.ascontiguousarray(u), np.ascontiguousarray(v))[0]
+    y, u, v = h2j_b200.split_planes(frame_bytes, w, h, chroma_format)
+    return orc.oracle_encode(np.ascontiguousarray(y), np.ascontiguousarray(u), np.ascontiguousarray(v), chroma_format=chroma_format)[0]
 
 
 def sample_indices(n, count, seed):
@@ -405,7 +407,7 @@ def sample_indices(n, count, seed):
     return sorted(pick)
 
 
-def device_pass(cx, enc, streams, d_frames, stride, fb, F, SB, NS, w, h, steps, warmup, profile_every, sample=0, min_seconds=0.0):
+def device_pass(cx, enc, streams, d_frames, stride, fb, F, SB, NS, w, h, steps, warmup, profile_every, sample=0, min_seconds=0.0, chroma_format=0):
     """The device-resident pass: `steps` steps of F frames in sub-batches of SB on NS slots, CUDA-event timed.  After
     the timed region `sample` frames of the LAST timed launch are fetched from the device and compared with the oracle.
     min_seconds > 0: keep stepping until the timed region has lasted that long (sustained figure)."""
@@ -478,7 +480,7 @@ def device_pass(cx, enc, streams, d_frames, stride, fb, F, SB, NS, w, h, steps, 
             bad = []
             for i in pick:
                 got = enc.read_device(last["d_out"] + i * last["cap"], int(last["sizes"][i]))
-                want = oracle_jpeg(d_frames[last["first_frame"] + i, :fb].cpu().numpy(), w, h)
+                want = oracle_jpeg(d_frames[last["first_frame"] + i, :fb].cpu().numpy(), w, h, chroma_format)
                 if got != want or int(last["status"][i]) != 0:
                     bad.append(last["first_frame"] + i)
             out["parity"] = {"frames": len(pick), "ok": not bad, "launch_frames": n_last, "differing": bad,
@@ -570,10 +572,10 @@ def e2e_pass(cx, d_frames, stride, fb, F, ESB, ENS, w, h, steps, warmup, max_jpe
     return res
 
 
-def kernel_table(dp, w, h, fb, SB, peak):
+def kernel_table(dp, w, h, fb, SB, peak, nblk=None):
     """Per-kernel averages and the algorithmic-bytes rates of DESIGN.md section 4."""
     mcu = ((w + 15) // 16) * ((h + 15) // 16)
-    nblk = mcu * 6
+    nblk = nblk or mcu * 6
     alg_bytes = algorithmic_bytes(w, h, fb, nblk, dp["avg_jpeg"], dp.get("avg_image_bytes"))
     per_kernel = {}
     for name, ms in dp["kernel_ms"].items():
@@ -610,27 +612,29 @@ def hbm_peak():
     return peak, ("MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
 
 
-def other_config(cx, w, h, F, ESB, a):
-    """One of BASELINE.json configs[3]'s geometries, outside the headline: device-resident and host-to-host throughput, the
-    FDCT kernel's roofline fraction and a parity sample of the timed launch."""
+def other_config(cx, w, h, F, ESB, a, chroma_format=0):
+    """One of BASELINE.json configs[3]'s geometries (or, with chroma_format, the encoder's other MCU geometries), outside
+    the headline: device-resident and host-to-host throughput, the FDCT kernel's roofline fraction and a parity sample of
+    the timed launch."""
     import h2j_b200
 
     torch = cx.torch
-    cap = 4 * 1024 * 1024 if w * h > 1920 * 1088 else 0
-    d_frames, fb, stride = make_frames_torch(F, w, h, cx.dev, seed0=1000 + cx.rank * F)
+    cap = 4 * 1024 * 1024 if w * h > 1920 * 1088 or chroma_format else 0
+    d_frames, fb, stride = make_frames_torch(F, w, h, cx.dev, seed0=1000 + cx.rank * F, chroma_format=chroma_format)
     torch.cuda.synchronize()
-    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=F, n_slots=1, device=cx.dev.index, profile=True, max_jpeg_bytes=cap)
+    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=F, n_slots=1, device=cx.dev.index, profile=True, max_jpeg_bytes=cap, chroma_format=chroma_format)
     st = torch.cuda.Stream(device=cx.dev)
     enc.set_stream(0, st.cuda_stream)
-    dp = device_pass(cx, enc, [st], d_frames, stride, fb, F, F, 1, w, h, steps=max(3, a.steps // 2), warmup=3, profile_every=2, sample=6)
+    dp = device_pass(cx, enc, [st], d_frames, stride, fb, F, F, 1, w, h, steps=max(3, a.steps // 2), warmup=3, profile_every=2, sample=6, chroma_format=chroma_format)
     peak, _ = hbm_peak()
-    per_kernel, _ = kernel_table(dp, w, h, fb, F, peak)
+    nblk_fmt = ((w + 7) // 8) * ((h + 15) // 16) * 6 if chroma_format == 2 else ((w + 15) // 16) * ((h + 15) // 16) * (8 if chroma_format == 1 else 6)
+    per_kernel, _ = kernel_table(dp, w, h, fb, F, peak, nblk=nblk_fmt)
     enc.close()
-    rec = {"width": w, "height": h, "frames_per_step_per_gpu": F, "value": dp["value"], "unit": UNIT, "mpixel_per_s": dp["value"] * w * h / 1e6,
+    rec = {"chroma_format": {0: "4:2:0", 1: "4:2:2", 2: "4:4:4"}[chroma_format], "width": w, "height": h, "frames_per_step_per_gpu": F, "value": dp["value"], "unit": UNIT, "mpixel_per_s": dp["value"] * w * h / 1e6,
            "ms_per_step": dp["dev_ms_max"] / dp["steps"], "steps": dp["steps"], "avg_jpeg_bytes": dp["avg_jpeg"], "parity_sampled": dp["parity"],
            "fdct_quant_kernel_frac": per_kernel.get("fdct_quant_kernel", {}).get("frac_of_hbm_peak"),
            "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in per_kernel.items()}}
-    if not a.no_e2e:
+    if not a.no_e2e and chroma_format == 0:
         e2e = e2e_pass(cx, d_frames, stride, fb, F, ESB, 4, w, h, steps=max(2, a.steps // 3), warmup=2, max_jpeg_bytes=cap, sample=3)
         rec["e2e"] = {k: e2e[k] for k in ("value", "unit", "h2d_gbs", "sub_batch", "slots", "parity_sampled") if k in e2e}
     del d_frames
@@ -884,11 +888,11 @@ def run_ours(a):
         del d_frames
         torch.cuda.empty_cache()
         others = []
-        for (ow, oh, oF, oESB) in ((3840, 2160, 256, 16), (1918, 1078, 512, 64)):
+        for (ow, oh, oF, oESB, ofmt) in ((3840, 2160, 256, 16, 0), (1918, 1078, 512, 64, 0), (1920, 1080, 512, 64, 1), (1920, 1080, 512, 64, 2)):
             try:
-                others.append(other_config(cx, ow, oh, oF, oESB, a))
+                others.append(other_config(cx, ow, oh, oF, oESB, a, chroma_format=ofmt))
             except Exception as ex:
-                others.append({"width": ow, "height": oh, "error": str(ex)})
+                others.append({"width": ow, "height": oh, "chroma_format": ofmt, "error": str(ex)})
 
     if rank == 0:
         line = {
