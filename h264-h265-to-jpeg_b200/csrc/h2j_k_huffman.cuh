@@ -34,36 +34,18 @@ __device__ long long g_k3_clocks[16];
 // sorted at the same time -- by two threads -- with the result the sequential order gives.  qsort_range() is the
 // reference's loop body for one range; qsort_replay() runs the ranges of one recursion depth side by side, a round per
 // depth (~2 log2 n rounds instead of ~n/2 partitions one after the other: 20 us -> ~2 us for an AC table of 60 symbols).
-constexpr int kQsortMaxRanges = 136;  // short ranges of one depth: at most num / 2 + 1 with num <= 257
-constexpr int kQsortWarpRange = 24;   // ranges of this many elements and more are partitioned by a whole warp
-constexpr int kQsortMaxWarpRanges = 16;
+constexpr int kQsortMaxRanges = 136;  // ranges of one depth: at most num / 2 + 1 with num <= 257
 
-struct QsortRounds {
-    unsigned short range[2][kQsortMaxRanges][2];     // ranges a single thread sorts
-    unsigned short wide[2][kQsortMaxWarpRanges][2];  // ranges a warp partitions
-    int count[3], wcount[3];  // ranges of this round / the next one / the one after (being cleared)
-};
-
-// hand a range to the next round
-__device__ __forceinline__ void qsort_push(QsortRounds *Q, int round, int s, int e)
+__device__ __forceinline__ void qsort_range(HuffPair *p, int start, int end, unsigned short (*next)[2], int *n_next)
 {
-    const int par = (round + 1) & 1, cnt = (round + 1) % 3;
-    if (e - s + 1 >= kQsortWarpRange) {
-        const int i = atomicAdd(&Q->wcount[cnt], 1);
-        Q->wide[par][i][0] = (unsigned short)s;
-        Q->wide[par][i][1] = (unsigned short)e;
-    } else {
-        const int i = atomicAdd(&Q->count[cnt], 1);
-        Q->range[par][i][0] = (unsigned short)s;
-        Q->range[par][i][1] = (unsigned short)e;
+    if (start >= end - 1) {  // two elements
+        const HuffPair a = p[start], b = p[end];
+        if (a.b > b.b) { p[start] = b; p[end] = a; }
+        return;
     }
-}
-
-// the reference's median of three: sorts p[start], p[mid], p[end] with ITS comparisons and swaps; returns checksort, the
-// pivot element ends up in p[mid]
-__device__ __forceinline__ int qsort_median3(HuffPair *p, int start, int mid, int end)
-{
     int checksort = 0;
+    int right = end - 2, left = start + 1;
+    const int mid = start + ((end - start) >> 1);
     HuffPair ps = p[start], pm = p[mid], pe = p[end];  // (start < mid < end: three different elements)
     auto swp = [](HuffPair &x, HuffPair &y) { const HuffPair t = x; x = y; y = t; };
     if (ps.b > pe.b) {
@@ -78,25 +60,12 @@ __device__ __forceinline__ int qsort_median3(HuffPair *p, int start, int mid, in
         checksort = 0;
     }
     p[start] = ps;
-    p[mid] = pm;
     p[end] = pe;
-    return checksort;
-}
-
-// One range, one thread: the reference's loop body as it stands.
-__device__ __forceinline__ void qsort_range(HuffPair *p, int start, int end, QsortRounds *Q, int round)
-{
-    if (start >= end - 1) {  // two elements
-        const HuffPair a = p[start], b = p[end];
-        if (a.b > b.b) { p[start] = b; p[end] = a; }
+    if (start == end - 2) {
+        p[mid] = pm;
         return;
     }
-    int right = end - 2, left = start + 1;
-    const int mid = start + ((end - start) >> 1);
-    const int checksort = qsort_median3(p, start, mid, end);
-    if (start == end - 2) return;
     // SWAP(end[-1], *mid): the pivot waits at end - 1 (mid <= end - 2 here)
-    const HuffPair pm = p[mid];
     p[mid] = p[end - 1];
     p[end - 1] = pm;
     const int pivot = pm.b;
@@ -145,134 +114,49 @@ __device__ __forceinline__ void qsort_range(HuffPair *p, int start, int end, Qso
         while (m < end && p[m].b <= p[m + 1].b) m++;
         if (m == end) return;
     }
-    if (start < right) qsort_push(Q, round, start, right);
-    if (left + 1 < end) qsort_push(Q, round, left + 1, end);
+    if (start < right) {
+        const int i = atomicAdd(n_next, 1);
+        next[i][0] = (unsigned short)start;
+        next[i][1] = (unsigned short)right;
+    }
+    if (left + 1 < end) {
+        const int i = atomicAdd(n_next, 1);
+        next[i][0] = (unsigned short)(left + 1);
+        next[i][1] = (unsigned short)end;
+    }
 }
 
-// One range, one warp (all 32 lanes call it with the same arguments).  The reference's partition loop -- left scan to the
-// next key >= pivot, right scan to the next key <= pivot, swap, repeat until the scans cross -- swaps the k-th stopper
-// from the left (A_k: positions with key >= pivot, ascending) with the k-th stopper from the right (B_k: positions with key
-// <= pivot, descending) for as long as A_k <= B_k: an element a swap has moved lies behind the scan that moved it, so no
-// scan decision ever depends on a swap.  Both lists are ballots over the range; every lane that holds an A_k finds its
-// B_k (k-th set bit from the top) and swaps its pair -- all pairs at once, they are disjoint.  Where the scans end follows
-// from the last pair and the next stopper from the left.  (Checked against the sequential loop on 200 k random arrays with
-// ties before it went on the GPU; the parity tests compare every DHT byte.)
-__device__ void qsort_range_warp(HuffPair *p, int start, int end, QsortRounds *Q, int round, int lane)
-{
-    const unsigned full = 0xffffffffu;
-    const int mid = start + ((end - start) >> 1);
-    int checksort = 0;
-    if (lane == 0) {
-        checksort = qsort_median3(p, start, mid, end);
-        const HuffPair pm = p[mid];  // SWAP(end[-1], *mid)
-        p[mid] = p[end - 1];
-        p[end - 1] = pm;
-    }
-    checksort = __shfl_sync(full, checksort, 0);
-    __syncwarp();
-    const int pivot = p[end - 1].b;
-    const int lo0 = start + 1, hi0 = end - 2, nw = (hi0 - lo0 + 32) >> 5;  // chunks of 32 positions (at most 8)
-    unsigned GE[8], LE[8];
-    int n_le = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        GE[w] = LE[w] = 0;
-        if (w < nw) {
-            const int pos = lo0 + 32 * w + lane;
-            const bool valid = pos <= hi0;
-            const int key = valid ? p[pos].b : 0;
-            GE[w] = __ballot_sync(full, valid && key >= pivot);
-            LE[w] = __ballot_sync(full, valid && key <= pivot);
-            n_le += __popc(LE[w]);
-        }
-    }
-    int t = 0, a_last = 0, b_last = 0, before = 0;  // pairs swapped, the last pair, stoppers from the left in earlier chunks
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        if (w < nw) {
-            const int pos = lo0 + 32 * w + lane;
-            const bool in_a = (GE[w] >> lane) & 1u;
-            const int k = before + __popc(GE[w] & ((1u << lane) - 1u));
-            int partner = -1;
-            if (in_a && k < n_le) {  // B_k: the k-th set bit of LE counted from the top
-                int rem = k;
-#pragma unroll
-                for (int v = 7; v >= 0; v--) {
-                    if (v < nw && partner < 0) {
-                        const int c = __popc(LE[v]);
-                        if (rem < c) partner = lo0 + 32 * v + (int)__fns(LE[v], 31, -(rem + 1));
-                        else rem -= c;
-                    }
-                }
-            }
-            const bool cond = in_a && partner >= 0 && pos <= partner;
-            const unsigned m = __ballot_sync(full, cond);
-            if (m) {
-                const int src = 31 - __clz(m);
-                a_last = __shfl_sync(full, pos, src);
-                b_last = __shfl_sync(full, partner, src);
-            }
-            t += __popc(m);
-            if (cond && pos != partner) {
-                const HuffPair x = p[pos], y = p[partner];
-                p[pos] = y;
-                p[partner] = x;
-            }
-            before += __popc(GE[w]);
-        }
-    }
-    __syncwarp();
-    int left = t ? a_last + 1 : lo0, right = t ? b_last - 1 : hi0;
-    if (left <= right) {  // one more pair of scans, without a swap: to the next stopper from the left, or until they cross
-        int at = -1, rem = t;
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-            if (v < nw && at < 0) {
-                const int c = __popc(GE[v]);
-                if (rem < c) at = lo0 + 32 * v + (int)__fns(GE[v], 0, rem + 1);
-                else rem -= c;
-            }
-        }
-        left = (at >= 0 && at <= right) ? at : right + 1;
-        right = left - 1;
-    }
-    if (lane == 0) {  // SWAP(end[-1], *left)
-        const HuffPair x = p[end - 1], y = p[left];
-        p[end - 1] = y;
-        p[left] = x;
-    }
-    __syncwarp();
-    if (checksort && (mid == left - 1 || mid == left)) {  // the reference's "already sorted" shortcut
-        bool ok = true;
-        for (int m = start + lane; m < end; m += 32) ok = ok && p[m].b <= p[m + 1].b;
-        if (__all_sync(full, ok)) return;
-    }
-    if (lane == 0) {
-        if (start < right) qsort_push(Q, round, start, right);
-        if (left + 1 < end) qsort_push(Q, round, left + 1, end);
-    }
-}
+struct QsortRounds {
+    unsigned short range[2][kQsortMaxRanges][2];
+    int count[3];  // ranges of this round / the next one / the one after (being cleared)
+};
 
 __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(128) : "memory"); }
 
+// Measured and dropped: ranges of 24 and more keys partitioned by a whole warp (the stoppers of both scans as ballots, the
+// k-th from the left swapped with the k-th from the right, all pairs at once -- exact, it passed the whole suite): an AC
+// table of 60 symbols took 10.6 + 10.8 us for its two sorts instead of 10.9 + 7.3 (finding the k-th set bit per lane and
+// the extra warp synchronisations cost what the shorter scans saved).
 // all kHuffGroup threads of the group call this; p[0 .. num + 2] must exist
 __device__ void qsort_replay(HuffPair *p, int num, QsortRounds *Q, int gt, int group)
 {
     if (gt == 0) {
-        for (int i = 0; i < 3; i++) Q->count[i] = Q->wcount[i] = 0;
-        if (num > 1) qsort_push(Q, -1, 0, num - 1);
+        Q->range[0][0][0] = 0;
+        Q->range[0][0][1] = (unsigned short)(num - 1);
+        Q->count[0] = num > 1 ? 1 : 0;
+        Q->count[1] = 0;
+        Q->count[2] = 0;
     }
     group_sync(group);
-    // short range i goes to thread (i % 4) * 32 + i / 4: the first ranges of a round land in different warps (threads of one
-    // warp that sort different ranges take turns at every divergent step); wide range i goes to warp i % 4
-    const int lane = gt & 31, warp = gt >> 5;
-    const int my_first = (lane << 2) | warp;
+    // range i goes to thread (i % 4) * 32 + i / 4: the first ranges of a round land in different warps (threads of one warp
+    // that sort different ranges take turns at every divergent step)
+    const int my_first = ((gt & 31) << 2) | (gt >> 5);
     for (int round = 0;; round++) {
-        const int n = Q->count[round % 3], nwide = Q->wcount[round % 3];
-        if (n == 0 && nwide == 0) break;
-        if (gt == 0) Q->count[(round + 2) % 3] = Q->wcount[(round + 2) % 3] = 0;
-        for (int i = warp; i < nwide; i += kHuffGroup / 32) qsort_range_warp(p, Q->wide[round & 1][i][0], Q->wide[round & 1][i][1], Q, round, lane);
-        for (int i = my_first; i < n; i += kHuffGroup) qsort_range(p, Q->range[round & 1][i][0], Q->range[round & 1][i][1], Q, round);
+        const int n = Q->count[round % 3];
+        if (n == 0) break;
+        if (gt == 0) Q->count[(round + 2) % 3] = 0;
+        for (int i = my_first; i < n; i += kHuffGroup)
+            qsort_range(p, Q->range[round & 1][i][0], Q->range[round & 1][i][1], Q->range[(round + 1) & 1], &Q->count[(round + 1) % 3]);
         group_sync(group);
 #ifdef H2J_K3_CLOCKS
         if (gt == 0) g_k3_clocks[15] = round + 1;  // rounds of the last sort
