@@ -914,6 +914,12 @@ def run_ours(a):
         }
         emit_line(line)
     if world > 1:
+        dist.barrier()
+        if local_rank == 0:  # the device plan of this launch (device_plan) has been read by everybody
+            try:
+                os.unlink(os.path.join(tempfile.gettempdir(), f"h2j_bench_devices_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}.json"))
+            except OSError:
+                pass
         dist.destroy_process_group()
 
 
