@@ -187,8 +187,13 @@ __device__ __forceinline__ int fetch_pred_rowsum(const BlockFetch &F, const Plan
     return s;
 }
 
+#ifdef H2J_FDCT_MAXNREG  // experiment: an explicit register cap instead of the bound derived from resident CTAs
+#define H2J_FDCT_BOUNDS __maxnreg__(H2J_FDCT_MAXNREG)
+#else
+#define H2J_FDCT_BOUNDS __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS)
+#endif
 template <bool NV12>
-__global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
+__global__ void H2J_FDCT_BOUNDS fdct_quant_kernel(const uint8_t *__restrict__ frames, FrameLayout L,
                                                                      FrameState *__restrict__ state,
                                                                      const FrameTab *__restrict__ tabs,
                                                                      uint32_t *__restrict__ images,  // [frame][images_cap] tile images
