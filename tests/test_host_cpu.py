@@ -64,3 +64,38 @@ def test_host_paths_fail_loudly_and_terminate_without_a_gpu(tmp_path, capfd):
     log = capfd.readouterr().out
     assert "h2j_create failed" in log and ("pinned allocation" in log or sum(accepted) == 21)
     assert lib.h2j_host_devices_in_use() == 0
+
+
+def test_stream_copy_is_a_memcpy():
+    """h2j_stream_copy (non-temporal stores where the CPU has AVX2) against numpy on every head / tail alignment."""
+    import h2j_b200
+
+    lib = h2j_b200.load_library()
+    lib.h2j_stream_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.h2j_stream_copy.restype = None
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, 1 << 20, dtype=np.uint8)
+    for n in (0, 1, 31, 32, 33, 127, 128, 129, 4095, 4096, 4097, 70001, 262144, 1000003):
+        for so in (0, 1, 7, 13):
+            for do in (0, 3, 16, 29):
+                if so + n > src.size:
+                    continue
+                dst = np.full(n + 64, 0xEE, np.uint8)
+                lib.h2j_stream_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
+                assert (dst[do: do + n] == src[so: so + n]).all(), (n, so, do)
+                assert (dst[:do] == 0xEE).all() and (dst[do + n:] == 0xEE).all(), (n, so, do)
+
+
+def test_dropin_library_exports_the_reference_surface():
+    """The drop-in (the reference's Decoder.cpp + JNI bridge over this repo's Encoder) loads without a GPU and exports what
+    the reference's library exports -- IDecoder::getInstance, the JNI entry -- plus the batch scope."""
+    so = os.path.join(ROOT, "h264-h265-to-jpeg_b200", "lib", "libH265ToJpeg_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("drop-in library not built (needs /root/reference at build time)")
+    lib = C.CDLL(so)
+    for name in ("_ZN8IDecoder11getInstanceEv", "Java_com_autonavi_socol_occtiltedserver_service_H265DecodeService_decode",
+                 "h2j_host_batch_begin", "h2j_host_batch_end", "h2j_host_configure", "h2j_host_devices_in_use", "dropin_h265_to_jpeg",
+                 "dropin_loop", "_ZN7Encoder8yuv2JpegEP7AVFrame"):
+        assert hasattr(lib, name), name
+    # the reference's own Encoder machinery is NOT in it (no second encoder hiding behind the class)
+    assert not hasattr(lib, "_ZN7Encoder19constructOutputDataEv")
