@@ -110,3 +110,18 @@ def test_range_conversion_fixed_qscale_and_refusals(orc):
             assert ei.value.status == h2j_b200.ERR_UNSUPPORTED
             with pytest.raises(h2j_b200.H2JError):
                 e.convert_pad(y, u, v, 0)
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_randomised_geometries_and_contents(orc, fmt):
+    """sizes and contents drawn at random (seeded): every width / height residue of the MCU grid, sparse and dense blocks"""
+    import h2j_b200
+
+    rng = np.random.default_rng(1000 + fmt)
+    kinds = ["textured", "noise", "blocks", "const", "binary", "ff"]
+    with h2j_b200.Encoder(max_width=400, max_height=300, max_batch=1, n_slots=1, chroma_format=fmt, max_jpeg_bytes=4 * 1024 * 1024) as e:
+        for i in range(40):
+            w, h = int(rng.integers(2, 400)), int(rng.integers(2, 300))
+            kind = kinds[int(rng.integers(0, len(kinds)))]
+            y, u, v = orc.synth_planes_fmt(w, h, fmt, kind, seed=int(rng.integers(0, 1 << 30)), amp=int(rng.integers(1, 128)))
+            assert e.yuv2jpeg(y, u, v) == orc.oracle_encode(y, u, v, chroma_format=fmt)[0], (fmt, w, h, kind, i)
