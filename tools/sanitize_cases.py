@@ -21,6 +21,18 @@ for (w, h, kind, amp, fq, rm) in cases:
     good = all(j == want for j in res.jpegs) and one == want
     print(w, h, kind, "ok" if good else "MISMATCH", len(want))
     ok = ok and good
+# the other chroma formats (single-component roles; 4:2:2's four-unit tiles), several tiles per CTA on a partial last tile
+for fmt in (1, 2):
+    for (w, h, kind, amp) in ((322, 242, "textured", 40), (131, 77, "noise", 80), (641, 479, "textured", 25)):
+        y, u, v = orc.synth_planes_fmt(w, h, fmt, kind, seed=w + fmt, amp=amp)
+        with h2j_b200.Encoder(max_width=w, max_height=h, max_batch=3, n_slots=1, chroma_format=fmt, max_jpeg_bytes=8 << 20) as e:
+            e.set_knob("fdct_tiles_per_cta", 3)
+            res = e.encode_batch(np.stack([orc.pack_i420(y, u, v)] * 3), w, h)
+            one = e.yuv2jpeg(y, u, v)
+        want = orc.oracle_encode(y, u, v, chroma_format=fmt)[0]
+        good = all(j == want for j in res.jpegs) and one == want
+        print("fmt", fmt, w, h, kind, "ok" if good else "MISMATCH", len(want))
+        ok = ok and good
 # NV12 device input and a frame whose scan is dense with 0xFF bytes (stuffing) / has units larger than a window
 import torch
 w, h = 322, 242
