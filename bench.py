@@ -642,6 +642,63 @@ def other_config(cx, w, h, F, ESB, a, chroma_format=0):
     return rec
 
 
+def nv12_record(cx, w, h, F, a):
+    """Row f2 in the driver-run line: NV12 frames as a hardware decoder leaves them in HBM (luma and interleaved Cb/Cr
+    planes at a 256-byte aligned pitch, the chroma plane behind the luma rows rounded up to 16), read in place by
+    h2j_submit_device_nv12; device-resident throughput and frames of the timed launch against the oracle's JPEG of the
+    equivalent planar frame."""
+    import h2j_b200
+
+    torch = cx.torch
+    d_frames, fb, stride = make_frames_torch(F, w, h, cx.dev, seed0=3000 + cx.rank * F)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    pitch = (max(w, 2 * cw) + 255) // 256 * 256
+    uv_off = pitch * ((h + 15) // 16 * 16)
+    nstride = (uv_off + pitch * ch + 255) // 256 * 256
+    nv = torch.zeros((F, nstride), dtype=torch.uint8, device=cx.dev)
+    nv[:, : pitch * h].view(F, h, pitch)[:, :, :w] = d_frames[:, : w * h].view(F, h, w)
+    uv = nv[:, uv_off: uv_off + pitch * ch].view(F, ch, pitch)
+    uv[:, :, 0: 2 * cw: 2] = d_frames[:, w * h: w * h + cw * ch].view(F, ch, cw)
+    uv[:, :, 1: 2 * cw: 2] = d_frames[:, w * h + cw * ch: fb].view(F, ch, cw)
+    torch.cuda.synchronize()
+    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=F, n_slots=1, device=cx.dev.index)
+    st = torch.cuda.Stream(device=cx.dev)
+    enc.set_stream(0, st.cuda_stream)
+    main = torch.cuda.current_stream(cx.dev)
+    steps = max(3, a.steps // 2)
+
+    def step():
+        enc.submit_device_nv12(0, nv.data_ptr(), nstride, pitch, uv_off, F, w, h)
+        return enc.collect_device(0)
+
+    for _ in range(3):
+        step()
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    st.wait_stream(main)
+    for _ in range(steps):
+        d_out, cap, sizes, status = step()
+    main.wait_stream(st)
+    e1.record(main)
+    torch.cuda.synchronize()
+    cx.barrier()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    bad = []
+    pick = sample_indices(F, 6, seed=F + 12)
+    for i in pick:
+        got = enc.read_device(d_out + i * cap, int(sizes[i]))
+        if got != oracle_jpeg(d_frames[i, :fb].cpu().numpy(), w, h) or int(status[i]) != 0:
+            bad.append(i)
+    enc.close()
+    del nv, d_frames
+    torch.cuda.empty_cache()
+    return {"input": f"NV12 in HBM, read in place (pitch {pitch}, chroma plane at row {uv_off // pitch})", "width": w, "height": h, "frames_per_step_per_gpu": F,
+            "value": cx.world * F * steps / (ms / 1000.0), "unit": UNIT, "steps": steps,
+            "parity_sampled": {"frames": len(pick), "ok": not bad, "differing": bad,
+                               "what": "JPEG bytes of frames of the last timed launch vs the oracle's JPEG of the planar frame with the same samples"}}
+
+
 def single_frame_record(cx, w, h, d_frames, stride, fb):
     """The reference's own call shape (Encoder::yuv2Jpeg, one picture): host planes in, JPEG bytes out, synchronous."""
     import h2j_b200
@@ -895,6 +952,13 @@ def run_ours(a):
             except Exception as ex:
                 others.append({"width": ow, "height": oh, "chroma_format": ofmt, "error": str(ex)})
 
+    nv12 = None
+    if not a.no_other_configs:
+        try:
+            nv12 = nv12_record(cx, w, h, 512, a)
+        except Exception as ex:
+            nv12 = {"error": str(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": dp["steps"], "warmup": a.warmup,
@@ -911,7 +975,7 @@ def run_ours(a):
                                                   "(its stock path); the GPU arm's e2e ends in pinned host memory"},
             "clocks": clocks, "e2e": e2e, "sustained": sustained, "two_stream": overlap, "gpu_launches": dp["launches"],
             "wall_ms_per_step": 1000 * dp["wall_s"] / dp["steps"],
-            "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu, "single_frame": single, "dropin": dropin, "other_configs": others,
+            "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu, "single_frame": single, "dropin": dropin, "other_configs": others, "nv12_device_input": nv12,
         }
         emit_line(line)
     if world > 1:
