@@ -713,6 +713,20 @@ def single_frame_record(cx, w, h, d_frames, stride, fb):
             t0 = time.perf_counter()
             e.yuv2jpeg_into(y, u, v)
             ts.append(time.perf_counter() - t0)
+        # the same call with the planes in page-locked memory (a decoder whose frame pool is pinned): no staging copy
+        pin = h2j_b200.PinnedBuffer(fb)
+        pin.array[:] = frame
+        py, pu, pv = h2j_b200.split_planes(pin.array, w, h)
+        tp = []
+        for _ in range(20):
+            e.yuv2jpeg_into(py, pu, pv)
+        for _ in range(200):
+            t0 = time.perf_counter()
+            e.yuv2jpeg_into(py, pu, pv)
+            tp.append(time.perf_counter() - t0)
+        tp.sort()
+        del py, pu, pv
+        pin.free()
         # batch of one, device resident
         cx.torch.cuda.synchronize()
         for _ in range(20):
@@ -726,6 +740,7 @@ def single_frame_record(cx, w, h, d_frames, stride, fb):
     ts.sort()
     return {"what": f"h2j_encode_frame: one {w}x{h} picture, pageable host planes in, JPEG bytes out, synchronous (the Encoder::yuv2Jpeg call shape)",
             "ms_median": 1000 * ts[len(ts) // 2], "ms_p10": 1000 * ts[len(ts) // 10], "ms_p90": 1000 * ts[len(ts) * 9 // 10],
+            "ms_median_pinned_planes": 1000 * tp[len(tp) // 2],
             "batch1_device_resident_fps": 1.0 / dt, "parity_ok": got == oracle_jpeg(frame, w, h)}
 
 

@@ -908,6 +908,24 @@ int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int s
         plane(planes[0], strides[0], 0, width, L.y_pitch, height);
         plane(planes[1], strides[1], (size_t)L.u_off, fcw, L.c_pitch, fch);
         plane(planes[2], strides[2], (size_t)L.v_off, fcw, L.c_pitch, fch);
+        // Planes that already live in page-locked memory (h2j_alloc_pinned, cudaHostAlloc, cudaHostRegister by the caller -- a
+        // decoder whose frame buffers come from such a pool) are uploaded from where they are: no staging copy, one strided
+        // DMA per plane.  The host copy is three quarters of the call for pageable planes.
+        auto pinned = [](const void *p) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            return at.type == cudaMemoryTypeHost;
+        };
+        static const bool no_direct = getenv("H2J_NO_DIRECT_UPLOAD") != nullptr;  // measurement knob
+        if (!no_direct && pinned(planes[0]) && pinned(planes[1]) && pinned(planes[2])) {
+            CU(e, cudaMemcpy2DAsync(sl.d_frames, L.y_pitch, planes[0], strides[0], width, height, cudaMemcpyHostToDevice, sl.stream));
+            CU(e, cudaMemcpy2DAsync(sl.d_frames + L.u_off, L.c_pitch, planes[1], strides[1], fcw, fch, cudaMemcpyHostToDevice, sl.stream));
+            CU(e, cudaMemcpy2DAsync(sl.d_frames + L.v_off, L.c_pitch, planes[2], strides[2], fcw, fch, cudaMemcpyHostToDevice, sl.stream));
+            n_pieces = 0;
+        }
         cudaError_t up_err = cudaSuccess;
         auto upload = [&](int i) {
             const cudaError_t ce = cudaMemcpyAsync(sl.d_frames + pieces[i].dev_off, sl.h_stage + pieces[i].dev_off, pieces[i].dev_bytes, cudaMemcpyHostToDevice, sl.stream);

@@ -100,7 +100,9 @@ int h2j_device_count(void);
  * Encoder::yuv2Jpeg() (reference src/Encoder.cpp:104).  planes/strides follow AVFrame.data/.linesize for
  * an 8-bit 4:2:0 planar frame: plane 0 is width x height, planes 1/2 are ceil(width/2) x ceil(height/2) (for an encoder
  * created with another chroma_format: ceil(width/2) x height at 4:2:2, width x height at 4:4:4).
- * Uses slot 0; the planes are staged through pinned memory and copied asynchronously.
+ * Uses slot 0; the planes are staged through pinned memory and copied asynchronously.  Planes that are page-locked already
+ * (allocated with h2j_alloc_pinned / cudaHostAlloc or registered with cudaHostRegister) are uploaded from where they are,
+ * without the staging copy (which is most of the call's time for pageable planes).
  */
 int h2j_encode_frame(h2j_encoder *e, const uint8_t *const planes[3], const int strides[3], int width, int height,
                      uint8_t *out, size_t out_capacity, size_t *out_size);

@@ -197,3 +197,24 @@ def test_rate_control_beyond_the_lookup_table(orc):
         info = e.frame_info(0, 0)
     assert info.qscale == 25 and info.mb_var_sum == dbg.mb_var_sum
     assert got == want
+
+
+def test_single_frame_from_pinned_planes_skips_the_staging_copy(enc, orc):
+    """h2j_encode_frame with planes in page-locked memory (strided, as an AVFrame from a pinned pool would be): uploaded from
+    where they are; same bytes as from pageable planes."""
+    import h2j_b200
+
+    w, h = 1918, 1078  # odd width: pitched device layout, strided 2-D copies
+    y, u, v = orc.synth_planes(w, h, "textured", seed=31, amp=33)
+    ys, cs = 1920 + 64, 960 + 32
+    buf = h2j_b200.PinnedBuffer(ys * h + 2 * cs * ((h + 1) // 2))
+    a = buf.array
+    py = a[: ys * h].reshape(h, ys)[:, :w]
+    pu = a[ys * h: ys * h + cs * ((h + 1) // 2)].reshape((h + 1) // 2, cs)[:, : (w + 1) // 2]
+    pv = a[ys * h + cs * ((h + 1) // 2):].reshape((h + 1) // 2, cs)[:, : (w + 1) // 2]
+    py[:], pu[:], pv[:] = y, u, v
+    want = orc.oracle_encode(y, u, v)[0]
+    assert enc.yuv2jpeg(py, pu, pv) == want
+    assert enc.yuv2jpeg(y, u, v) == want
+    del py, pu, pv, a
+    buf.free()
