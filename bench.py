@@ -642,6 +642,47 @@ def other_config(cx, w, h, F, ESB, a, chroma_format=0):
     return rec
 
 
+def camera_record(cx, F, a):
+    """The encoder on the reference's OWN picture: test/img/img01.h264 (a 1920x1080 camera frame), decoded once on the host by
+    the libavcodec the reference vendors (oracle/_ref), F copies of it device-resident.  The bench frames are synthetic texture
+    with ~2.6 x the non-zero levels of this picture; this record says what the same kernels do on camera content.  Six frames
+    of the timed launch are compared with the oracle."""
+    import h2j_b200
+    from tests.support import oracle as orc
+
+    fix = os.path.join(ROOT, "oracle", "_ref", "fixtures", "img01.h264")
+    if not orc.have_reference() or not os.path.exists(fix):
+        return {"unavailable": "the compiled reference (its decoder) or the reference's test picture is not present on this box"}
+    torch = cx.torch
+    R = orc.reference()
+    yb = np.zeros(4096 * 4096, np.uint8); ub = np.zeros(2048 * 2048, np.uint8); vb = np.zeros_like(ub)
+    info = np.zeros(8, np.int64)
+    if R.ref_decode_first_frame(fix.encode(), yb.ctypes.data, ub.ctypes.data, vb.ctypes.data, yb.size, info.ctypes.data) != 1:
+        return {"error": "the reference's decoder did not return a frame"}
+    w, h = int(info[0]), int(info[1])
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    frame = np.concatenate([yb[: w * h], ub[: cw * ch], vb[: cw * ch]])
+    fb = frame.size
+    stride = (fb + 255) // 256 * 256
+    d_frames = torch.zeros((F, stride), dtype=torch.uint8, device=cx.dev)
+    d_frames[:, :fb] = torch.from_numpy(frame).to(cx.dev)[None, :]
+    torch.cuda.synchronize()
+    enc = h2j_b200.Encoder(max_width=w, max_height=h, max_batch=F, n_slots=1, device=cx.dev.index, profile=True)
+    st = torch.cuda.Stream(device=cx.dev)
+    enc.set_stream(0, st.cuda_stream)
+    dp = device_pass(cx, enc, [st], d_frames, stride, fb, F, F, 1, w, h, steps=max(3, a.steps // 2), warmup=3, profile_every=2, sample=6)
+    peak, _ = hbm_peak()
+    per_kernel, _ = kernel_table(dp, w, h, fb, F, peak)
+    enc.close()
+    del d_frames
+    torch.cuda.empty_cache()
+    return {"what": f"{F} copies of the reference's test picture img01.h264 ({w}x{h}, decoded by the reference's libavcodec), device-resident",
+            "width": w, "height": h, "frames_per_step_per_gpu": F, "value": dp["value"], "unit": UNIT, "ms_per_step": dp["dev_ms_max"] / dp["steps"],
+            "avg_jpeg_bytes": dp["avg_jpeg"], "parity_sampled": dp["parity"],
+            "fdct_quant_kernel_frac": per_kernel.get("fdct_quant_kernel", {}).get("frac_of_hbm_peak"),
+            "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in per_kernel.items()}}
+
+
 def nv12_record(cx, w, h, F, a):
     """Row f2 in the driver-run line: NV12 frames as a hardware decoder leaves them in HBM (luma and interleaved Cb/Cr
     planes at a 256-byte aligned pitch, the chroma plane behind the luma rows rounded up to 16), read in place by
@@ -974,6 +1015,13 @@ def run_ours(a):
         except Exception as ex:
             nv12 = {"error": str(ex)}
 
+    camera = None
+    if not a.no_other_configs and world == 1:
+        try:
+            camera = camera_record(cx, 512, a)
+        except Exception as ex:
+            camera = {"error": str(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": dp["steps"], "warmup": a.warmup,
@@ -990,7 +1038,7 @@ def run_ours(a):
                                                   "(its stock path); the GPU arm's e2e ends in pinned host memory"},
             "clocks": clocks, "e2e": e2e, "sustained": sustained, "two_stream": overlap, "gpu_launches": dp["launches"],
             "wall_ms_per_step": 1000 * dp["wall_s"] / dp["steps"],
-            "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu, "single_frame": single, "dropin": dropin, "other_configs": others, "nv12_device_input": nv12,
+            "roofline": roof, "kernels": per_kernel, "cpu_baseline": cpu, "single_frame": single, "dropin": dropin, "other_configs": others, "nv12_device_input": nv12, "camera_content": camera,
         }
         emit_line(line)
     if world > 1:
