@@ -245,10 +245,14 @@ __global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(Fram
         bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
         bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
         bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
+    }
+    if (tid == 32) {
         // CTAs are dispatched in linear order, so this one asks for the image of a CTA that starts a fraction of a CTA
         // lifetime (~4 us) from now to be brought into L2; that CTA's bulk copy then finds it there.  Worth 1.3 % of the
         // kernel (any distance from 384 to 2048 CTAs measures the same, 4096 is 12 % slower): most of the wait behind
-        // the mbarrier is not DRAM latency.
+        // the mbarrier is not DRAM latency.  (Thread 32, not thread 0: everybody waits at the barrier below for thread 0 to
+        // have set up the mbarrier and the copies -- 10 % of the kernel's stall samples sat there -- and the division for
+        // the prefetch address was part of that wait: 2.757 -> 2.731 ms per 2048 frames.)
         const long long lin = (long long)f * gridDim.x + tile + kEntPrefetchDistance;
         if (lin < (long long)gridDim.x * gridDim.y) {
             const long long f2 = lin / gridDim.x, t2 = lin - f2 * gridDim.x;
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(Fram
     static_assert((kWarps * kWarpWinStride) % 4 == 0 && (kImageBytes + kEntTabBytes) % 16 == 0, "windows are cleared 16 bytes at a time");
     for (int i = tid; i < kWarps * kWarpWinStride / 4; i += kThreads) reinterpret_cast<uint4 *>(s_win_all)[i] = make_uint4(0, 0, 0, 0);  // while the copies are on their way
     __syncthreads();  // barrier initialised, windows cleared (clearing only the words a unit needs, once its length is
-                      // known, executes fewer instructions but measured 1 % slower: here it hides under the copy)
+                      // known, executes fewer instructions but measured 1 % slower: here it hides under the copy; the barrier
+                      // right behind mbar_init, every warp clearing its own window: 2.742 ms against 2.731)
 
     // ---- from here on the warp is on its own ----
     const int u = tile * kWarps + warp;                     // unit index inside the frame
