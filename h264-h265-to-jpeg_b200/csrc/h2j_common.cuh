@@ -133,7 +133,9 @@ struct alignas(16) FrameTab {
     uint8_t intra[64];       // raster order (inspection)
     uint32_t hcode[4][256];  // ((code << nb) << 5) | (code length + nb), nb = symbol & 15: the mantissa bits K4a appends;
                              // classes: 0 DC luma, 1 DC chroma, 2 AC luma, 3 AC chroma
-                             // (16-byte aligned inside the struct: K4 fetches the four tables with one bulk copy)
+                             // The two DC tables (16 entries each) live in hcode[1][224..255] (dc_code_table), right in front of
+                             // the AC tables: 16-byte aligned, K4a fetches all four with one bulk copy; hcode[0] and the rest
+                             // of hcode[1] are not used
     uint8_t bits[4][17];
     uint8_t vals[4][256];
     int nvals[4];
@@ -146,6 +148,9 @@ struct alignas(16) FrameTab {
     long long stuffed_ff;
     long long jpeg_bytes;
 };
+
+constexpr int kDcCodeOff = 256 - 32;  // first word of the DC code tables inside hcode[1]
+__host__ __device__ inline uint32_t *dc_code_table(FrameTab *T, int cls) { return T->hcode[1] + kDcCodeOff + 16 * cls; }
 
 // Per-frame state zeroed by one memset at the start of every batch.
 struct FrameState {

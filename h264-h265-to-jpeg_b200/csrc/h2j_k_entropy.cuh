@@ -214,7 +214,7 @@ __host__ __device__ constexpr int ent_smem_bytes(int fmt)
     return fmt_roles(fmt) * kSubImageBytes + kEntTabBytes + fmt_roles(fmt) * (kWarpWinStride + kUnitBlocks * kSlotStride) * 4;
 }
 constexpr int kEntSmemBytes = ent_smem_bytes(kFmt420);
-static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0, "hcode must be bulk-copyable");
+static_assert(offsetof(FrameTab, hcode) % 16 == 0 && sizeof(FrameTab) % 16 == 0 && (kDcCodeOff * 4) % 16 == 0, "the code tables must be bulk-copyable");
 
 // grid (tiles_per_frame, frames); FMT = the chroma format (h2j_common.cuh): a tile is 96 blocks (three units) at 4:2:0 and
 // 4:4:4, 128 blocks (four units) at 4:2:2; one thread per block, one warp per unit
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(Fram
         const uint32_t *src = images + ((long long)f * images_cap + tile) * kImageWords;
         mbar_expect_tx(&s_bar, kImageBytes + kEntTabBytes);
         bulk_g2s(s_img, src, kImageBytes, &s_bar);
-        bulk_g2s(s_hdc, tabs[f].hcode[0], 64, &s_bar);
-        bulk_g2s(s_hdc + 16, tabs[f].hcode[1], 64, &s_bar);
-        bulk_g2s(s_hac, tabs[f].hcode[2], 2048, &s_bar);
+        // DC luma, DC chroma, AC luma, AC chroma: contiguous (K3 puts the DC tables right in front of the AC tables), one copy
+        // instead of three -- thread 0's set-up is what the CTA's other threads wait for at the barrier below (2.733 -> 2.708 ms)
+        bulk_g2s(s_hdc, dc_code_table(tabs + f, 0), kEntTabBytes, &s_bar);
     }
     if (tid == 32) {
         // CTAs are dispatched in linear order, so this one asks for the image of a CTA that starts a fraction of a CTA

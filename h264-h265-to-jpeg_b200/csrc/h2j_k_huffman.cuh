@@ -208,7 +208,7 @@ __device__ __forceinline__ int group_excl_scan(int v, int gt, int group, int *wa
 
 // One table, executed by the 128 threads of `group` (gt = thread index inside the group).
 __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScratch *S, int gt, int group, uint8_t *g_bits, uint8_t *g_vals,
-                                int *g_nvals, uint32_t *g_hcode)
+                                int *g_nvals, uint32_t *g_hcode, int n_hcode)  // n_hcode: entries of the code table (16 DC, 256 AC)
 {
     // ---- ff_mjpeg_encode_huffman_close: used symbols in increasing value order, plus the dummy (256, 0) ----
     K3_STAMP(0);
@@ -304,7 +304,7 @@ __device__ void build_one_table(const unsigned int *__restrict__ hist, HuffScrat
     // ---- BITS / HUFFVAL, then ff_mjpeg_build_huffman_codes ----
     for (int i = gt; i < 256; i += kHuffGroup) {
         g_vals[i] = i < nval ? (uint8_t)S->distinct[i].a : 0;
-        g_hcode[i] = 0;
+        if (i < n_hcode) g_hcode[i] = 0;
         if (i < nval) atomicAdd(&S->bits_cnt[S->distinct[i].b], 1u);
     }
     group_sync(group);
@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(kHuffGroup) huffman_kernel(FrameLayout L, Fram
     if (tid == 0) scratch.stamp_on = (table == 2 && f == 0);
     __syncthreads();
 #endif
-    build_one_table(state[f].hist[table], &scratch, tid, 0, T->bits[table], T->vals[table], &T->nvals[table], T->hcode[table]);
+    // the two DC code tables (16 entries each) go right in front of the AC tables -- into the unused tail of hcode[1] -- so that
+    // K4a fetches all four with ONE bulk copy
+    uint32_t *hc = table < 2 ? dc_code_table(T, table) : T->hcode[table];
+    build_one_table(state[f].hist[table], &scratch, tid, 0, T->bits[table], T->vals[table], &T->nvals[table], hc, table < 2 ? 16 : 256);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(&state[f].k3_done, 1u) == 3u;
