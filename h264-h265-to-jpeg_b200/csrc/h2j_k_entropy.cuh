@@ -328,15 +328,20 @@ __global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(Fram
         // ---- 2. merge the slots into the warp's window ----
         if (valid) {
             if (len <= (unsigned)kSlotBits) {
+                // window word k of the block = the slot's words k - 1 and k funnelled together: one OR per window word (nw + 1 of
+                // them) instead of two per slot word
                 const int nw = (int)((len + 31) >> 5);
+                const unsigned sh = off & 31;
+                unsigned int *w = win + (off >> 5);
+                unsigned prev = 0;
                 for (int i = 0; i < nw; i++) {
-                    const unsigned src = slot[i];
-                    const unsigned dest = off + 32u * i, sh = dest & 31;
-                    unsigned int *w = win + (dest >> 5);
-                    atomicOr(w, src >> sh);
-                    const unsigned spill = sh ? src << (32 - sh) : 0u;
-                    if (spill) atomicOr(w + 1, spill);
+                    const unsigned cur = slot[i];
+                    const unsigned o = __funnelshift_r(cur, prev, sh);
+                    if (o) atomicOr(w + i, o);
+                    prev = cur;
                 }
+                const unsigned tail = __funnelshift_r(0u, prev, sh);  // (sh == 0: nothing left over)
+                if (tail) atomicOr(w + nw, tail);
             } else {
                 BitSink sink;
                 sink.init(win, off);
@@ -352,7 +357,9 @@ __global__ void __launch_bounds__(fmt_tile_blocks(FMT)) entropy_walk_kernel(Fram
         // multiple of four are zeros inside the unit's own place)
         uint4 *dst4 = reinterpret_cast<uint4 *>(st + pos);
         const uint4 *src4 = reinterpret_cast<const uint4 *>(win);
-        for (unsigned i = lane; i * 4 < nwords; i += 32) dst4[i] = src4[i];
+        const unsigned nquads = (nwords + 3) >> 2;
+        if ((unsigned)lane < nquads) dst4[lane] = src4[lane];  // (a unit of natural content: a dozen quads)
+        for (unsigned i = lane + 32; i < nquads; i += 32) dst4[i] = src4[i];
     } else {
         unsigned pos;
         const unsigned n_fit = claim(lane == 0 ? fixed_words + atomicAdd(&stage_alloc[f], nwords) : 0u, pos);
