@@ -126,15 +126,18 @@ struct SlotSink {  // MSB-first into the lane's private slot; keeps counting (an
     int fill;
     int widx;
     __device__ __forceinline__ void init(unsigned int *s) { slot = s; acc = 0; fill = 0; widx = 0; }
+    // No branch, no predicate: in a walking warp nearly every put completes a word in SOME lane, so the branch around the store
+    // was taken anyway and only added its own instructions (and a reconvergence point) to every put.  len <= 27 and fill <= 31 on
+    // entry, so fill + len < 64: the completed word is acc >> ((fill + len) & 31), and fill & 31 is what stays.
     __device__ __forceinline__ void put(unsigned bits, int len)
     {
         acc = (acc << len) | bits;
-        fill += len;
-        if (fill >= 32) {
-            if (widx < kSlotWords) slot[widx] = (unsigned)(acc >> (fill - 32));
-            widx++;
-            fill -= 32;
-        }
+        const int f2 = fill + len;
+        fill = f2 & 31;
+        // stored whether the word is complete or not: an incomplete one is stored again when it is (or by flush()); words past
+        // the slot's capacity land in the slot's spare word (kSlotStride = kSlotWords + 1)
+        slot[min(widx, kSlotWords)] = (unsigned)(acc >> fill);
+        widx += f2 >> 5;
     }
     __device__ __forceinline__ unsigned bits() const { return (unsigned)(widx * 32 + fill); }
     __device__ __forceinline__ void flush() { if (fill > 0 && widx < kSlotWords) slot[widx] = (unsigned)(acc << (32 - fill)); }
