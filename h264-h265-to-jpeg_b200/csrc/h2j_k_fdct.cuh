@@ -35,6 +35,8 @@
 
 namespace h2j {
 
+constexpr int kHistDummy = 257;  // s_hist: where the statistics walk counts a level that is not there (count_if)
+
 // What a thread needs to know about the plane its block lives in: fixed for the whole kernel.
 struct PlaneRef {
     const uint8_t *P;
@@ -202,7 +204,7 @@ __global__ void H2J_FDCT_BOUNDS fdct_quant_kernel(const uint8_t *__restrict__ fr
     __shared__ __align__(128) uint32_t s_img[2][kSubImageWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
-    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_hist[256 + 8];  // (+ kHistDummy, the word nobody reads)
     __shared__ unsigned int s_dchist[16];
 
     const int f = blockIdx.y;
@@ -337,6 +339,16 @@ __global__ void H2J_FDCT_BOUNDS fdct_quant_kernel(const uint8_t *__restrict__ fr
                 zrl += (unsigned)run >> 4;
                 atomicAdd(&hist[1 + (((run & 15) << 4) | (int)top)], 1u);
             };
+            // the same for a level a lane may not have, WITHOUT a branch: in a walking warp some lane has it, so the warp ran
+            // the branch's body anyway plus the branch and its reconvergence point (K2 5.458 -> 5.376 ms per 2048 frames); a lane
+            // without the level counts into a word nobody reads
+            auto count_if = [&](bool have, int k, int below, int val) {
+                const int run = k - below - 1;
+                unsigned top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(val)));
+                zrl += have ? (unsigned)run >> 4 : 0u;
+                atomicAdd(&hist[have ? 1 + (((run & 15) << 4) | (int)top) : kHistDummy], 1u);
+            };
             unsigned lo = mask_lo;
             const int top_lo = lo ? 31 - __clz(lo) : 0;  // highest non-zero position below 32 (0: none but the DC)
 #if H2J_K2_WALK
@@ -355,9 +367,9 @@ __global__ void H2J_FDCT_BOUNDS fdct_quant_kernel(const uint8_t *__restrict__ fr
                 const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1), k2 = 31 - __clz(b2), k3 = 31 - __clz(b3);  // -1: absent
                 const int v0 = (int)lv[2 * k0], v1 = (int)lv[2 * max(k1, 0)];
                 count(k0, below, v0);
-                if (b1) count(k1, k0, v1);
-                if (H2J_K2_WALK >= 3 && b2) count(k2, k1, (int)lv[2 * max(k2, 0)]);
-                if (H2J_K2_WALK >= 4 && b3) count(k3, k2, (int)lv[2 * max(k3, 0)]);
+                count_if(b1 != 0, k1, k0, v1);
+                if (H2J_K2_WALK >= 3) count_if(b2 != 0, k2, k1, (int)lv[2 * max(k2, 0)]);
+                if (H2J_K2_WALK >= 4) count_if(b3 != 0, k3, k2, (int)lv[2 * max(k3, 0)]);
                 below = 31 - __clz(b0 | b1 | b2 | b3);
             }
 #else

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_fm
     __shared__ __align__(128) uint32_t s_img[2][kSubImageWords];
     __shared__ __align__(16) int s_q[64];
     __shared__ __align__(16) int s_bq[64];
-    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_hist[256 + 8];  // (+ kHistDummy)
     __shared__ unsigned int s_dchist[16];
 
     const int f = blockIdx.y;
@@ -161,7 +161,13 @@ __global__ void __launch_bounds__(kFdctThreads, H2J_FDCT_MIN_CTAS) fdct_quant_fm
                 const int k0 = 31 - __clz(b0), k1 = 31 - __clz(b1);
                 const int v0 = (int)lv[2 * k0], v1 = (int)lv[2 * max(k1, 0)];
                 count(k0, below, v0);
-                if (b1) count(k1, k0, v1);
+                {  // a level the lane may not have, without a branch (fdct_quant_kernel's count_if): counted into a word nobody reads
+                    const int run = k1 - k0 - 1;
+                    unsigned top;
+                    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(abs(v1)));
+                    zrl += b1 ? (unsigned)run >> 4 : 0u;
+                    atomicAdd(&s_hist[b1 ? 1 + (((run & 15) << 4) | (int)top) : kHistDummy], 1u);
+                }
                 below = 31 - __clz(b0 | b1);
             }
             int prev = top_lo;
