@@ -25,8 +25,11 @@ __device__ __forceinline__ void stuff_put(unsigned int *img, unsigned q, unsigne
     const unsigned s = (q & 3u) * 8u;
     unsigned int *w = img + (q >> 2);
     const unsigned x0 = lo << s, x1 = __funnelshift_l(lo, hi, s), x2 = s ? hi >> (32u - s) : 0u;
-    if (x0) atomicOr(w, x0);
-    if (x1) atomicOr(w + 1, x1);
+    // the first two without a test: a test is a branch with its reconvergence point around ONE instruction, x0 is hardly ever
+    // zero and x1 only when the item starts on a word boundary (ORing a zero in is harmless; w + 1 is inside the image, whose
+    // size allows for w + 2); the third piece only exists behind an inserted zero
+    atomicOr(w, x0);
+    atomicOr(w + 1, x1);
     if (x2) atomicOr(w + 2, x2);
 }
 
